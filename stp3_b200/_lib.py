@@ -1,0 +1,63 @@
+"""ctypes loader for libstp3_b200.so (the C ABI declared in include/stp3_b200.h).
+
+There is NO fallback: if the library is missing or was not built, using an op raises.  The library is
+built in-tree (stp3_b200/csrc/Makefile, driven by __graft_entry__.build()) so that the .so travels with the
+repository snapshot to the GPU box.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstp3_b200.so")
+_lib = None
+
+# name -> (restype, argtypes); lists every symbol of include/stp3_b200.h (tests/test_abi.py checks that).
+# Device pointers travel as integers (c_void_p).
+_V = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_SZ = ctypes.c_size_t
+_FP = ctypes.POINTER(ctypes.c_float)
+SIGNATURES = {
+    "stp3_abi_version": (_I, []),
+    "stp3_build_info": (ctypes.c_char_p, []),
+    "stp3_last_error": (ctypes.c_char_p, []),
+    "stp3_lift_splat_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
+                                 _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,
+                                 _V, _V, _V, _SZ, _V, _I, _V]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into stp3_b200/libstp3_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libstp3_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(stp3_b200 has no CPU or PyTorch fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"{what} failed ({code}): {lib().stp3_last_error().decode()}")

@@ -1,0 +1,31 @@
+// Shared helpers for libstp3_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/stp3_b200.h"
+
+namespace stp3 {
+
+// thread-local error text behind stp3_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define STP3_CHECK_ARG(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) return ::stp3::set_error(STP3_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define STP3_CUDA_OK(expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::stp3::set_error(STP3_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                               __FILE__, __LINE__);                                               \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace stp3

@@ -1,0 +1,94 @@
+"""Python entry points over the C ABI: tensors in, tensors out, current CUDA stream, no fallback."""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stp3_b200 ops run on CUDA tensors only (there is no CPU path)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _host3(v):
+    a = torch.as_tensor(v, dtype=torch.float32, device="cpu").reshape(3)
+    return (ctypes.c_float * 3)(*[float(x) for x in a])   # exact: a python float holds every fp32
+
+
+class Workspace:
+    """Grow-only device scratch buffer reused between calls (the lift-splat's L2-resident scatter grid)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_default_ws = Workspace()
+
+
+def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
+               discount: float, *, feat_channels_last: bool = False, out_channels_last: bool = False,
+               use_depth_distribution: bool = True, return_ranks: bool = False, pool_sum: bool = False,
+               workspace: Optional[Workspace] = None, out: Optional[torch.Tensor] = None):
+    """Fused lift (softmax-depth (x) context) + ego-aligned voxel pooling + temporal discount.
+
+      feat          (B,S,N,C,Hf,Wf) or, with feat_channels_last, (B,S,N,Hf,Wf,C)
+      depth_logits  (B,S,N,D,Hf,Wf)
+      cam_M/cam_t/ego_R/ego_t/xs/ys/ds  see utils.geometry.lift_matrices / frustum_axes
+      bev_off, bev_res (3,) float (host values); bev_dim (3,) int
+    Returns out (B,S,C,X,Y) [or (B,S,X,Y,C)], and optionally ranks (B,S,N,D,Hf,Wf) int32 and pool sums (B,S,C).
+    Semantics: stp3/models/stp3.py:186-301 of the reference."""
+    _require_cuda(feat, depth_logits, cam_M)
+    dev = feat.device
+    if feat_channels_last:
+        B, S, N, Hf, Wf, C = feat.shape
+    else:
+        B, S, N, C, Hf, Wf = feat.shape
+    D = ds.numel()
+    nx, ny, nz = (int(v) for v in bev_dim)
+    feat = _f32c(feat)
+    depth_logits = _f32c(depth_logits) if depth_logits is not None else None
+    if use_depth_distribution:
+        assert depth_logits is not None and tuple(depth_logits.shape) == (B, S, N, D, Hf, Wf), "depth_logits shape"
+    cam_M, cam_t, ego_R, ego_t = (_f32c(t.to(dev)) for t in (cam_M, cam_t, ego_R, ego_t))
+    xs, ys, ds = (_f32c(t.to(dev)) for t in (xs, ys, ds))
+    assert cam_M.shape == (B, S, N, 3, 3) and cam_t.shape == (B, S, N, 3)
+    assert ego_R.shape == (B, S, 3, 3) and ego_t.shape == (B, S, 3)
+    assert xs.numel() == Wf and ys.numel() == Hf
+    L = _lib.lib()
+    need = L.stp3_lift_splat_workspace_bytes(B, S, C, nx, ny)
+    ws = (workspace or _default_ws).get(need, dev)
+    oshape = (B, S, nx, ny, C) if out_channels_last else (B, S, C, nx, ny)
+    if out is None:
+        out = torch.empty(oshape, dtype=torch.float32, device=dev)
+    else:
+        assert tuple(out.shape) == oshape and out.is_contiguous() and out.dtype == torch.float32
+    ranks = torch.empty((B, S, N, D, Hf, Wf), dtype=torch.int32, device=dev) if return_ranks else None
+    psum = torch.zeros((B, S, C), dtype=torch.float32, device=dev) if pool_sum else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        code = L.stp3_lift_splat_fwd(
+            feat.data_ptr(), int(feat_channels_last), depth_logits.data_ptr() if depth_logits is not None else None,
+            cam_M.data_ptr(), cam_t.data_ptr(), ego_R.data_ptr(), ego_t.data_ptr(),
+            xs.data_ptr(), ys.data_ptr(), ds.data_ptr(), _host3(bev_off), _host3(bev_res),
+            nx, ny, nz, float(discount), B, S, N, D, Hf, Wf, C, int(use_depth_distribution),
+            ranks.data_ptr() if ranks is not None else None, psum.data_ptr() if psum is not None else None,
+            ws.data_ptr(), ws.numel(), out.data_ptr(), int(out_channels_last), stream)
+    _lib.check(code, "stp3_lift_splat_fwd")
+    res = (out,)
+    if return_ranks:
+        res += (ranks,)
+    if pool_sum:
+        res += (psum,)
+    return res if len(res) > 1 else out
