@@ -251,7 +251,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
-            "gpu_launches": 2 * K * 2,   # scatter + finalize kernels per step, resident and e2e timed regions
+            "gpu_launches": 2 * K * 2,   # scatter + finalize kernels per step (no memset), resident and e2e timed regions
             "roofline": {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
                          "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": None,

@@ -61,10 +61,15 @@ const char* stp3_last_error(void);
  *                 out_layout==1: (B,S,nx,ny,C) fp32  [channels-last, consumed by the temporal block kernels]
  *   pool_sum      optional (B,S,C) fp32: sum over the nx*ny cells of out[b,t,c] (feeds the pyramid-pooling branch
  *                 of TemporalBlock, temporal.py:408-423); must be zero-initialised by the caller.
- *   workspace     >= stp3_lift_splat_workspace_bytes(...) bytes, 256-byte aligned
+ *   workspace     >= stp3_lift_splat_workspace_bytes(...) bytes, 256-byte aligned.  It holds the channels-last
+ *                 fp32 scatter grid (B,S,nx*ny,C) and a per-pillar occupancy map.  It must be ALL ZERO on entry:
+ *                 clear it once with stp3_lift_splat_workspace_init() after allocating it; every successful
+ *                 stp3_lift_splat_fwd leaves it zero again (the finalize kernel re-zeroes exactly the pillars it
+ *                 read), so no per-call memset is needed.  After a failed call, re-initialise it.
  * nz must be 1 (the reference's squeeze(0) at stp3.py:298 assumes it).
  */
 size_t stp3_lift_splat_workspace_bytes(int B, int S, int C, int nx, int ny);
+int stp3_lift_splat_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_logits,
                         const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,

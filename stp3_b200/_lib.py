@@ -24,6 +24,7 @@ SIGNATURES = {
     "stp3_build_info": (ctypes.c_char_p, []),
     "stp3_last_error": (ctypes.c_char_p, []),
     "stp3_lift_splat_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "stp3_lift_splat_workspace_init": (_I, [_V, _SZ, _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
                                  _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,
                                  _V, _V, _V, _SZ, _V, _I, _V]),

@@ -1,16 +1,19 @@
 // Fused lift-splat for sm_100a.
 //
 //   K1  lift_splat_scatter_kernel : one CTA per (b, t, camera, tile of TW image columns)
-//         phase A  depth logits of the tile -> shared memory, softmax over D in place (never leaves the SM)
+//         phase A  depth logits and context features of the tile -> shared memory (coalesced tile loads),
+//                  softmax over D in place (probabilities never leave the SM; the 371 MB/sample outer product of
+//                  the reference, stp3.py:216, is never materialised)
 //         phase B  frustum point -> ego frame -> sequential ego-motion warp -> voxel rank, with the reference's
-//                  exact fp32 operation order (no FMA, IEEE division, truncation), rank staged beside the prob
+//                  exact fp32 operation order (no FMA, IEEE division, truncation); rank staged beside the prob
 //         phase C  outer product + pooling: a warp owns one image column; lanes own channel pairs and keep the
-//                  column's context features in registers; walking the column for every depth bin is a
-//                  segmented reduction over equal pillar ranks (all rows of a level camera fall into the same
-//                  pillar), flushed with one coalesced red.global.add.v2.f32 per lane per segment into a
-//                  channels-last (b,t,pillar,C) fp32 grid that stays L2 resident
+//                  column's context features in registers; walking the column for every depth bin is a segmented
+//                  reduction over equal pillar ranks (all rows of a level camera fall into the same pillar),
+//                  flushed with one coalesced red.global.add.v2.f32 per lane per segment into a channels-last
+//                  (b,t,pillar,C) fp32 grid, plus one byte in a per-pillar occupancy map
 //   K2  bev_finalize_kernel : temporal discount recurrence out[t] = out[t-1]*discount + grid[t] and the
-//         channels-last -> (C,X,Y) transpose through shared memory, coalesced both ways
+//         channels-last -> (C,X,Y) transpose through shared memory.  Reads (and re-zeroes) only the occupied
+//         pillars, so the scatter grid is left clean for the next call and never needs a memset.
 //
 // Reference semantics: /root/reference/stp3/models/stp3.py:186-301, stp3/utils/geometry.py:299-318.
 #include <cstdint>
@@ -22,6 +25,7 @@ namespace stp3 {
 constexpr int kMaxFrames = 8;      // receptive field S supported by the in-kernel pose chain
 constexpr int kScatterThreads = 256;
 constexpr int kHChunk = 32;        // image rows whose features a lane keeps in registers at once
+constexpr int kCChunk = 64;        // channels staged in shared memory at once (2 per lane)
 
 struct LiftSplatParams {
   const float* feat;
@@ -42,7 +46,8 @@ struct LiftSplatParams {
   int TW;        // image columns per CTA
   int tiles_w;   // ceil(Wf / TW)
   int32_t* ranks_out;
-  float* grid;   // (B,S,nx*ny*nz,C) fp32, zero on entry
+  float* grid;          // (B,S,nx*ny*nz,C) fp32, all-zero on entry
+  unsigned char* occ;   // (B,S,nx*ny*nz) bytes, all-zero on entry; set to 1 where the grid was written
 };
 
 // ((m0*x + m1*y) + m2*z) + t, every product and sum rounded to fp32 separately: bit-identical to the reference's
@@ -59,18 +64,26 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// shared-memory row of channel (c0 + cl) in the feature tile: the two channels of a lane (2*lane, 2*lane+1) live in
+// rows lane and lane+32, so that with an odd row stride the register fill of phase C is bank-conflict free
+__device__ __forceinline__ int feat_row(int cl) { return ((cl & 1) << 5) | (cl >> 1); }
+
 __global__ void __launch_bounds__(kScatterThreads, 2)
 lift_splat_scatter_kernel(const LiftSplatParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C, TW = p.TW;
   const int npix = Hf * TW;
   const int npts = D * npix;
+  const int fstride = npix | 1;                                    // odd row stride of the feature tile
   int2* s_pt = reinterpret_cast<int2*>(smem_raw);                  // [D][Hf][TW] {rank, prob bits}
-  float* s_mat = reinterpret_cast<float*>(s_pt + npts);            // camera 12 + (kMaxFrames-1) * 12 pose floats
+  float* s_feat = reinterpret_cast<float*>(s_pt + npts);           // [kCChunk rows][fstride]
+  float* s_mat = s_feat + kCChunk * fstride;                       // camera 12 + (kMaxFrames-1) * 12 pose floats
   float* s_ys = s_mat + 12 * kMaxFrames;                           // [Hf]
   float* s_ds = s_ys + Hf;                                         // [D]
+  float* s_red = s_ds + D;                                         // [blockDim] softmax partials
 
   const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
   int blk = blockIdx.x;
   const int tile = blk % p.tiles_w; blk /= p.tiles_w;
   const int n = blk % p.N; blk /= p.N;
@@ -84,18 +97,18 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   // ---- small per-CTA constants
   if (tid < 9) s_mat[tid] = p.cam_M[img * 9 + tid];
   if (tid >= 9 && tid < 12) s_mat[tid] = p.cam_t[img * 3 + tid - 9];
-  for (int i = tid; i < n_chain * 12; i += blockDim.x) {
+  for (int i = tid; i < n_chain * 12; i += nthr) {
     const int k = i / 12, e = i % 12;
     const int src = b * p.S + t + k;
     s_mat[12 + i] = e < 9 ? p.ego_R[src * 9 + e] : p.ego_t[src * 3 + e - 9];
   }
-  for (int i = tid; i < Hf; i += blockDim.x) s_ys[i] = p.ys[i];
-  for (int i = tid; i < D; i += blockDim.x) s_ds[i] = p.ds[i];
+  for (int i = tid; i < Hf; i += nthr) s_ys[i] = p.ys[i];
+  for (int i = tid; i < D; i += nthr) s_ds[i] = p.ds[i];
 
-  // ---- phase A: logits -> smem
+  // ---- phase A: logits tile -> smem
   if (p.use_depth) {
     const float* dsrc = p.depth + (size_t)img * D * Hf * Wf;
-    for (int i = tid; i < npts; i += blockDim.x) {
+    for (int i = tid; i < npts; i += nthr) {
       const int wl = i % TW;
       const int dh = i / TW;                     // d*Hf + h
       const int w = w0 + wl;
@@ -105,22 +118,52 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   }
   __syncthreads();
   if (p.use_depth) {
-    // softmax over D, one thread per pixel of the tile (stp3.py:215)
-    for (int pix = tid; pix < npix; pix += blockDim.x) {
+    // softmax over D (stp3.py:215): `parts` threads share one pixel, each owning a slice of the depth axis
+    const int npix_r = (npix + 31) & ~31;
+    const int parts = nthr / npix_r;
+    if (parts >= 1) {
+      const int pix = tid % npix_r, part = tid / npix_r;
+      const bool act = pix < npix && part < parts;
+      const int dchunk = (D + parts - 1) / parts;
+      const int da = part * dchunk, db = min(D, da + dchunk);
       float mx = -INFINITY;
-      for (int d = 0; d < D; ++d) mx = fmaxf(mx, __int_as_float(s_pt[d * npix + pix].y));
+      if (act) for (int d = da; d < db; ++d) mx = fmaxf(mx, __int_as_float(s_pt[d * npix + pix].y));
+      s_red[tid] = mx;
+      __syncthreads();
+      if (act) for (int q = 0; q < parts; ++q) mx = fmaxf(mx, s_red[q * npix_r + pix]);
+      __syncthreads();
       float sum = 0.f;
-      for (int d = 0; d < D; ++d) {
+      if (act) for (int d = da; d < db; ++d) {
         const float e = __expf(__int_as_float(s_pt[d * npix + pix].y) - mx);
         s_pt[d * npix + pix].y = __float_as_int(e);
         sum += e;
       }
-      const float inv = __frcp_rn(sum);
-      for (int d = 0; d < D; ++d)
-        s_pt[d * npix + pix].y = __float_as_int(__int_as_float(s_pt[d * npix + pix].y) * inv);
+      s_red[tid] = sum;
+      __syncthreads();
+      if (act) {
+        float tot = 0.f;
+        for (int q = 0; q < parts; ++q) tot += s_red[q * npix_r + pix];
+        const float inv = __frcp_rn(tot);
+        for (int d = da; d < db; ++d)
+          s_pt[d * npix + pix].y = __float_as_int(__int_as_float(s_pt[d * npix + pix].y) * inv);
+      }
+    } else {  // very tall tiles: one thread per pixel, several pixels per thread
+      for (int pix = tid; pix < npix; pix += nthr) {
+        float mx = -INFINITY;
+        for (int d = 0; d < D; ++d) mx = fmaxf(mx, __int_as_float(s_pt[d * npix + pix].y));
+        float sum = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float e = __expf(__int_as_float(s_pt[d * npix + pix].y) - mx);
+          s_pt[d * npix + pix].y = __float_as_int(e);
+          sum += e;
+        }
+        const float inv = __frcp_rn(sum);
+        for (int d = 0; d < D; ++d)
+          s_pt[d * npix + pix].y = __float_as_int(__int_as_float(s_pt[d * npix + pix].y) * inv);
+      }
     }
   } else {
-    for (int i = tid; i < npts; i += blockDim.x) s_pt[i].y = __float_as_int(1.0f);  // stp3.py:218
+    for (int i = tid; i < npts; i += nthr) s_pt[i].y = __float_as_int(1.0f);  // stp3.py:218
   }
 
   // ---- phase B: voxel rank of every point of the tile (bit-exact with the reference CPU path)
@@ -128,7 +171,7 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
     const float offx = p.off[0], offy = p.off[1], offz = p.off[2];
     const float resx = p.res[0], resy = p.res[1], resz = p.res[2];
     const float fnx = (float)p.nx, fny = (float)p.ny, fnz = (float)p.nz;
-    for (int i = tid; i < npts; i += blockDim.x) {
+    for (int i = tid; i < npts; i += nthr) {
       const int wl = i % TW;
       const int dh = i / TW;
       const int h = dh % Hf;
@@ -158,24 +201,47 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
       s_pt[i].x = rank;
     }
   }
-  __syncthreads();
 
   // ---- phase C: outer product + segmented pooling.  work item = (column, depth slice); lanes = channel pairs
   const int warp = tid >> 5, lane = tid & 31;
-  const int nwarps = blockDim.x >> 5;
+  const int nwarps = nthr >> 5;
   const int dsplit = max(1, nwarps / TW);
   const int dper = (D + dsplit - 1) / dsplit;
   const size_t nvox = (size_t)p.nx * p.ny * p.nz;
   float* gbase = p.grid + (size_t)bt * nvox * C;
+  unsigned char* obase = p.occ + (size_t)bt * nvox;
   const bool vec_ok = (C % 2) == 0;
-  for (int item = warp; item < TW * dsplit; item += nwarps) {
-    const int wl = item % TW;
-    const int w = w0 + wl;
-    if (w >= Wf) continue;
-    const int d0 = (item / TW) * dper;
-    const int d1 = min(D, d0 + dper);
-    for (int c0 = 0; c0 < C; c0 += 64) {
-      const int c = c0 + 2 * lane;
+  for (int c0 = 0; c0 < C; c0 += kCChunk) {
+    // stage the context features of channels [c0, c0+64) of this tile (stp3.py:216 reads them D times)
+    __syncthreads();
+    if (p.feat_nhwc) {
+      for (int i = tid; i < kCChunk * npix; i += nthr) {
+        const int cl = i % kCChunk;
+        const int px = i / kCChunk;              // h*TW + wl
+        const int wl = px % TW, h = px / TW;
+        const int w = w0 + wl, c = c0 + cl;
+        float v = 0.f;
+        if (w < Wf && c < C) v = __ldg(p.feat + (((size_t)img * Hf + h) * Wf + w) * C + c);
+        s_feat[feat_row(cl) * fstride + px] = v;
+      }
+    } else {
+      for (int i = tid; i < kCChunk * npix; i += nthr) {
+        const int px = i % npix;
+        const int cl = i / npix;
+        const int wl = px % TW, h = px / TW;
+        const int w = w0 + wl, c = c0 + cl;
+        float v = 0.f;
+        if (w < Wf && c < C) v = __ldg(p.feat + (((size_t)img * C + c) * Hf + h) * Wf + w);
+        s_feat[feat_row(cl) * fstride + px] = v;
+      }
+    }
+    __syncthreads();
+    const int c = c0 + 2 * lane;
+    for (int item = warp; item < TW * dsplit; item += nwarps) {
+      const int wl = item % TW;
+      if (w0 + wl >= Wf) continue;
+      const int d0 = (item / TW) * dper;
+      const int d1 = min(D, d0 + dper);
       for (int h0 = 0; h0 < Hf; h0 += kHChunk) {
         float f0[kHChunk], f1[kHChunk];
 #pragma unroll
@@ -183,15 +249,8 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
           const int h = h0 + j;
           f0[j] = 0.f; f1[j] = 0.f;
           if (h < Hf) {
-            if (p.feat_nhwc) {
-              const float* src = p.feat + (((size_t)img * Hf + h) * Wf + w) * C + c;
-              if (c < C) f0[j] = __ldg(src);
-              if (c + 1 < C) f1[j] = __ldg(src + 1);
-            } else {
-              const float* src = p.feat + (((size_t)img * C + c) * Hf + h) * Wf + w;
-              if (c < C) f0[j] = __ldg(src);
-              if (c + 1 < C) f1[j] = __ldg(src + (size_t)Hf * Wf);
-            }
+            f0[j] = s_feat[lane * fstride + h * TW + wl];
+            f1[j] = s_feat[(lane + 32) * fstride + h * TW + wl];
           }
         }
         int cur = -1;
@@ -203,10 +262,13 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
             if (h0 + j < Hf) {
               const int2 v = row[j * TW];
               if (v.x != cur) {                      // warp-uniform: segment boundary
-                if (cur >= 0 && c < C) {
-                  float* dst = gbase + (size_t)cur * C + c;
-                  if (vec_ok) red_add_v2(dst, a0, a1);
-                  else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
+                if (cur >= 0) {
+                  if (c < C) {
+                    float* dst = gbase + (size_t)cur * C + c;
+                    if (vec_ok) red_add_v2(dst, a0, a1);
+                    else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
+                  }
+                  if (lane == 0 && c0 == 0) obase[cur] = 1;
                 }
                 cur = v.x; a0 = 0.f; a1 = 0.f;
               }
@@ -216,10 +278,13 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
             }
           }
         }
-        if (cur >= 0 && c < C) {
-          float* dst = gbase + (size_t)cur * C + c;
-          if (vec_ok) red_add_v2(dst, a0, a1);
-          else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
+        if (cur >= 0) {
+          if (c < C) {
+            float* dst = gbase + (size_t)cur * C + c;
+            if (vec_ok) red_add_v2(dst, a0, a1);
+            else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
+          }
+          if (lane == 0 && c0 == 0) obase[cur] = 1;
         }
       }
     }
@@ -227,47 +292,71 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 }
 
 // out[b,t] = out[b,t-1]*discount + grid[b,t]  (stp3.py:296, separate fp32 mul and add like the reference's
-// `bev_feature * discount + tmp`), written either channels-last (no transpose) or as (C, X*Y) through a
-// 32x32 shared-memory transpose.  grid: (B,S,nvox,C).  pool_sum (B,S,C) += sum over cells (optional).
+// `bev_feature * discount + tmp`), written either channels-last or as (C, X*Y) through a 32x32 shared-memory
+// transpose.  One CTA = 32 consecutive pillars of one sample, all channels, all frames.  Only occupied
+// (frame, pillar) rows of the grid are read; they are zeroed again and their occupancy byte cleared, which
+// leaves the workspace clean for the next call.  pool_sum (B,S,C) += sum over cells (optional).
 __global__ void __launch_bounds__(256)
-bev_finalize_kernel(const float* __restrict__ grid, float* __restrict__ out, float* __restrict__ pool_sum,
-                    int S, int C, int nvox, float discount, int out_nhwc) {
+bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, float* __restrict__ out,
+                    float* __restrict__ pool_sum, int S, int C, int nvox, float discount, int out_nhwc) {
   __shared__ float tile[32][33];
-  const int b = blockIdx.z;
+  const int b = blockIdx.y;
   const int p0 = blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;     // (32, 8)
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool use_tile = !out_nhwc || pool_sum != nullptr;
+  const int tx = threadIdx.x, ty = threadIdx.y;     // (32, 8); warp == ty
+  // occupancy bits of this warp's 4 pillars for every frame: bit (t*4 + k)
+  unsigned occ_bits = 0;
   for (int t = 0; t < S; ++t) {
-    const size_t bt = (size_t)b * S + t;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int pl = ty + 8 * k;                      // pillar within tile
-      const int pcell = p0 + pl, c = c0 + tx;
-      float v = 0.f;
-      if (pcell < nvox && c < C) v = grid[(bt * nvox + pcell) * C + c];
-      acc[k] = __fadd_rn(__fmul_rn(acc[k], discount), v);   // out-of-range entries stay exactly zero
-      if (out_nhwc && pcell < nvox && c < C) out[(bt * nvox + pcell) * C + c] = acc[k];
-      if (use_tile) tile[pl][tx] = acc[k];
+      const int pcell = p0 + ty + 8 * k;
+      if (pcell < nvox && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << (t * 4 + k);
     }
-    if (use_tile) {
-      __syncthreads();
-      if (!out_nhwc) {
+  }
+  __syncwarp();
+  if (tx == 0) {
+    for (int t = 0; t < S; ++t)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int cl = ty + 8 * k;
-          const int c = c0 + cl, pcell = p0 + tx;
-          if (c < C && pcell < nvox) out[(bt * C + c) * (size_t)nvox + pcell] = tile[tx][cl];
+      for (int k = 0; k < 4; ++k)
+        if (occ_bits & (1u << (t * 4 + k))) occ[((size_t)b * S + t) * nvox + p0 + ty + 8 * k] = 0;
+  }
+  const bool use_tile = !out_nhwc || pool_sum != nullptr;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c = c0 + tx;
+    for (int t = 0; t < S; ++t) {
+      const size_t bt = (size_t)b * S + t;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int pl = ty + 8 * k;                      // pillar within tile
+        const int pcell = p0 + pl;
+        float v = 0.f;
+        if ((occ_bits & (1u << (t * 4 + k))) && c < C) {
+          float* src = grid + (bt * nvox + pcell) * C + c;
+          v = *src;
+          *src = 0.f;
         }
+        acc[k] = __fadd_rn(__fmul_rn(acc[k], discount), v);   // out-of-range entries stay exactly zero
+        if (out_nhwc && pcell < nvox && c < C) out[(bt * nvox + pcell) * C + c] = acc[k];
+        if (use_tile) tile[pl][tx] = acc[k];
       }
-      if (pool_sum && ty == 0 && c0 + tx < C) {       // per-(b,t,c) spatial sum for the pyramid-pooling branch
-        float tot = 0.f;
+      if (use_tile) {
+        __syncthreads();
+        if (!out_nhwc) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) tot += tile[r][tx];
-        atomicAdd(pool_sum + bt * C + c0 + tx, tot);
+          for (int k = 0; k < 4; ++k) {
+            const int cl = ty + 8 * k;
+            const int cc = c0 + cl, pcell = p0 + tx;
+            if (cc < C && pcell < nvox) __stcs(out + (bt * C + cc) * (size_t)nvox + pcell, tile[tx][cl]);
+          }
+        }
+        if (pool_sum && ty == 0 && c < C) {       // per-(b,t,c) spatial sum for the pyramid-pooling branch
+          float tot = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) tot += tile[r][tx];
+          atomicAdd(pool_sum + bt * C + c, tot);
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
 }
@@ -276,9 +365,21 @@ bev_finalize_kernel(const float* __restrict__ grid, float* __restrict__ out, flo
 
 using namespace stp3;
 
+static size_t grid_bytes(int B, int S, int C, int nx, int ny) {
+  const size_t g = (size_t)B * S * nx * ny * C * sizeof(float);
+  return (g + 255) & ~(size_t)255;
+}
+
 extern "C" size_t stp3_lift_splat_workspace_bytes(int B, int S, int C, int nx, int ny) {
   if (B <= 0 || S <= 0 || C <= 0 || nx <= 0 || ny <= 0) return 0;
-  return (size_t)B * S * nx * ny * C * sizeof(float);
+  const size_t o = ((size_t)B * S * nx * ny + 255) & ~(size_t)255;
+  return grid_bytes(B, S, C, nx, ny) + o;
+}
+
+extern "C" int stp3_lift_splat_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  STP3_CHECK_ARG(workspace != nullptr, "stp3_lift_splat_workspace_init: null workspace");
+  STP3_CUDA_OK(cudaMemsetAsync(workspace, 0, workspace_bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return STP3_OK;
 }
 
 extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_logits,
@@ -315,19 +416,21 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   p.feat_nhwc = feat_layout; p.use_depth = use_depth_distribution;
   p.ranks_out = ranks_out;
   p.grid = static_cast<float*>(workspace);
+  p.occ = static_cast<unsigned char*>(workspace) + grid_bytes(B, S, C, nx, ny);
 
-  // tile width: as wide as shared memory allows (<= 8 columns), at least 1
+  // tile width: as wide as shared memory allows (<= 4 columns), at least 1
   int TW = 4;
   auto smem_for = [&](int tw) {
-    return (size_t)D * Hf * tw * sizeof(int2) + (size_t)(12 * kMaxFrames + Hf + D) * sizeof(float);
+    const int npix = Hf * tw;
+    return (size_t)D * npix * sizeof(int2) +
+           (size_t)(kCChunk * (npix | 1) + 12 * kMaxFrames + Hf + D + kScatterThreads) * sizeof(float);
   };
-  while (TW > 1 && smem_for(TW) > 100 * 1024) TW >>= 1;
+  while (TW > 1 && smem_for(TW) > 110 * 1024) TW >>= 1;
   const size_t smem = smem_for(TW);
   STP3_CHECK_ARG(smem <= 227 * 1024, "D*Hf = %d too large for one image column in shared memory", D * Hf);
   p.TW = TW;
   p.tiles_w = ceil_div(Wf, TW);
 
-  STP3_CUDA_OK(cudaMemsetAsync(workspace, 0, need, stream));
   STP3_CUDA_OK(cudaFuncSetAttribute(lift_splat_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nblk = (long long)B * S * N * p.tiles_w;
   STP3_CHECK_ARG(nblk < (1ll << 31), "grid too large");
@@ -335,8 +438,9 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   STP3_CUDA_OK(cudaGetLastError());
 
   const int nvox = nx * ny * nz;
-  dim3 fgrid(ceil_div(nvox, 32), ceil_div(C, 32), B), fblock(32, 8);
-  bev_finalize_kernel<<<fgrid, fblock, 0, stream>>>(p.grid, out, pool_sum, S, C, nvox, discount, out_layout);
+  STP3_CHECK_ARG(S * 4 <= 32, "S too large for the finalize occupancy mask");
+  dim3 fgrid(ceil_div(nvox, 32), B), fblock(32, 8);
+  bev_finalize_kernel<<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }

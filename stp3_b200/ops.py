@@ -31,7 +31,16 @@ class Workspace:
     def get(self, nbytes: int, device) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self.reset()
         return self.buf
+
+    def reset(self):
+        """Zero the buffer (required once after allocation, and after any failed call; see include/stp3_b200.h)."""
+        if self.buf is not None:
+            with torch.cuda.device(self.buf.device):
+                code = _lib.lib().stp3_lift_splat_workspace_init(
+                    self.buf.data_ptr(), self.buf.numel(), torch.cuda.current_stream(self.buf.device).cuda_stream)
+            _lib.check(code, "stp3_lift_splat_workspace_init")
 
 
 _default_ws = Workspace()
@@ -49,7 +58,7 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
       bev_off, bev_res (3,) float (host values); bev_dim (3,) int
     Returns out (B,S,C,X,Y) [or (B,S,X,Y,C)], and optionally ranks (B,S,N,D,Hf,Wf) int32 and pool sums (B,S,C).
     Semantics: stp3/models/stp3.py:186-301 of the reference."""
-    _require_cuda(feat, depth_logits, cam_M)
+    _require_cuda(feat, depth_logits)
     dev = feat.device
     if feat_channels_last:
         B, S, N, Hf, Wf, C = feat.shape
@@ -85,6 +94,8 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
             nx, ny, nz, float(discount), B, S, N, D, Hf, Wf, C, int(use_depth_distribution),
             ranks.data_ptr() if ranks is not None else None, psum.data_ptr() if psum is not None else None,
             ws.data_ptr(), ws.numel(), out.data_ptr(), int(out_channels_last), stream)
+    if code != 0:
+        (workspace or _default_ws).reset()
     _lib.check(code, "stp3_lift_splat_fwd")
     res = (out,)
     if return_ranks:
