@@ -12,8 +12,9 @@
 //                  flushed with one coalesced red.global.add.v2.f32 per lane per segment into a channels-last
 //                  (b,t,pillar,C) fp32 grid, plus one byte in a per-pillar occupancy map
 //   K2  bev_finalize_kernel : temporal discount recurrence out[t] = out[t-1]*discount + grid[t] and the
-//         channels-last -> (C,X,Y) transpose through shared memory.  Reads (and re-zeroes) only the occupied
-//         pillars, so the scatter grid is left clean for the next call and never needs a memset.
+//         channels-last -> (C,X,Y) transpose (lane = pillar, so stores are coalesced rows with no smem staging).
+//         Reads (and re-zeroes) only the occupied pillars, so the scatter grid is left clean for the next call
+//         and never needs a memset.
 //
 // Reference semantics: /root/reference/stp3/models/stp3.py:186-301, stp3/utils/geometry.py:299-318.
 #include <cstdint>
@@ -68,15 +69,37 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 // rows lane and lane+32, so that with an odd row stride the register fill of phase C is bank-conflict free
 __device__ __forceinline__ int feat_row(int cl) { return ((cl & 1) << 5) | (cl >> 1); }
 
+// flush one finished segment: lane owns channels (c, c+1) of pillar `rank`
+__device__ __forceinline__ void flush_segment(float* gbase, unsigned char* obase, int rank, int C, int c, bool vec_ok,
+                                              bool mark, float a0, float a1) {
+  if (c < C) {
+    float* dst = gbase + (size_t)rank * C + c;
+    if (vec_ok) red_add_v2(dst, a0, a1);
+    else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
+  }
+  if (mark) obase[rank] = 1;
+}
+
+// TW = image columns per CTA (compile time so that tile indexing is shifts and immediates).
+// Shared-memory tile layout (HP = Hf rounded up to 4 so that a column's probabilities are float4-readable):
+//   s_prob [D][TW][HP] f32   softmax(depth) of the tile, zero in the padding rows
+//   s_rank [D][TW][HP] i32   pillar rank or -1
+//   s_col  [D][TW]     i32   rank shared by the whole image column (the usual case: a level camera maps a column
+//                            of pixels at one depth into one pillar), -1 if the whole column is masked,
+//                            -2 if the column spans several pillars (segmented slow path)
+//   s_feat [64][npix|1] f32  context features of 64 channels, row permuted by feat_row()
+template <int TW>
 __global__ void __launch_bounds__(kScatterThreads, 2)
 lift_splat_scatter_kernel(const LiftSplatParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C, TW = p.TW;
+  const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C;
+  const int HP = (Hf + 3) & ~3;
   const int npix = Hf * TW;
-  const int npts = D * npix;
   const int fstride = npix | 1;                                    // odd row stride of the feature tile
-  int2* s_pt = reinterpret_cast<int2*>(smem_raw);                  // [D][Hf][TW] {rank, prob bits}
-  float* s_feat = reinterpret_cast<float*>(s_pt + npts);           // [kCChunk rows][fstride]
+  float* s_prob = reinterpret_cast<float*>(smem_raw);
+  int* s_rank = reinterpret_cast<int*>(s_prob + D * TW * HP);
+  int* s_col = s_rank + D * TW * HP;
+  float* s_feat = reinterpret_cast<float*>(s_col + D * TW);        // [kCChunk rows][fstride]
   float* s_mat = s_feat + kCChunk * fstride;                       // camera 12 + (kMaxFrames-1) * 12 pose floats
   float* s_ys = s_mat + 12 * kMaxFrames;                           // [Hf]
   float* s_ds = s_ys + Hf;                                         // [D]
@@ -94,6 +117,12 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   const int bt = b * p.S + t;
   const int n_chain = p.S - 1 - t;               // poses t .. S-2 applied in order (stp3.py:270-277)
 
+  // thread <-> pixel mapping shared by phases A and B: `parts` threads per pixel, each owning a slice of D
+  const int npix_r = (npix + 31) & ~31;
+  const int parts = max(1, nthr / npix_r);
+  const int my_part = (nthr / npix_r) <= 1 ? 0 : tid / npix_r;
+  const int dchunk = (D + parts - 1) / parts;
+
   // ---- small per-CTA constants
   if (tid < 9) s_mat[tid] = p.cam_M[img * 9 + tid];
   if (tid >= 9 && tid < 12) s_mat[tid] = p.cam_t[img * 3 + tid - 9];
@@ -104,102 +133,98 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   }
   for (int i = tid; i < Hf; i += nthr) s_ys[i] = p.ys[i];
   for (int i = tid; i < D; i += nthr) s_ds[i] = p.ds[i];
+  if (HP != Hf)                                                    // zero the padding rows once
+    for (int i = tid; i < D * TW * (HP - Hf); i += nthr) {
+      const int col = i / (HP - Hf), r = i % (HP - Hf);
+      s_prob[col * HP + Hf + r] = 0.f;
+      s_rank[col * HP + Hf + r] = -1;
+    }
+  __syncthreads();
 
-  // ---- phase A: logits tile -> smem
-  if (p.use_depth) {
-    const float* dsrc = p.depth + (size_t)img * D * Hf * Wf;
-    for (int i = tid; i < npts; i += nthr) {
-      const int wl = i % TW;
-      const int dh = i / TW;                     // d*Hf + h
-      const int w = w0 + wl;
-      const float v = w < Wf ? __ldg(dsrc + (size_t)dh * Wf + w) : 0.f;
-      s_pt[i].y = __float_as_int(v);
+  // ---- phases A + B, one pass over the pixels this thread owns
+  const float offx = p.off[0], offy = p.off[1], offz = p.off[2];
+  const float resx = p.res[0], resy = p.res[1], resz = p.res[2];
+  const float fnx = (float)p.nx, fny = (float)p.ny, fnz = (float)p.nz;
+  for (int px0 = 0; px0 < npix; px0 += (parts == 1 ? nthr : npix_r)) {
+    const int px = px0 + (parts == 1 ? tid : tid % npix_r);
+    const bool act = px < npix && my_part < parts;
+    const int wl = px % TW, h = px / TW;
+    const int w = w0 + wl;
+    const bool inb = act && w < Wf;
+    const int da = my_part * dchunk, db = act ? min(D, da + dchunk) : da;
+    float* prow = s_prob + wl * HP + h;          // + d*TW*HP
+    // A: logits -> smem, softmax over D (stp3.py:215)
+    if (p.use_depth) {
+      const float* dsrc = p.depth + ((size_t)img * D * Hf + h) * Wf + w;
+      float mx = -INFINITY;
+      for (int d = da; d < db; ++d) {
+        const float v = inb ? __ldg(dsrc + (size_t)d * Hf * Wf) : 0.f;
+        prow[d * TW * HP] = v;
+        mx = fmaxf(mx, v);
+      }
+      if (parts > 1) {
+        s_red[tid] = mx;
+        __syncthreads();
+        if (act) for (int q = 0; q < parts; ++q) mx = fmaxf(mx, s_red[q * npix_r + px - px0]);
+        __syncthreads();
+      }
+      float sum = 0.f;
+      for (int d = da; d < db; ++d) {
+        const float e = __expf(prow[d * TW * HP] - mx);
+        prow[d * TW * HP] = e;
+        sum += e;
+      }
+      if (parts > 1) {
+        s_red[tid] = sum;
+        __syncthreads();
+        sum = 0.f;
+        if (act) for (int q = 0; q < parts; ++q) sum += s_red[q * npix_r + px - px0];
+        __syncthreads();
+      }
+      const float inv = __frcp_rn(sum);
+      for (int d = da; d < db; ++d) prow[d * TW * HP] *= inv;
+    } else {
+      for (int d = da; d < db; ++d) prow[d * TW * HP] = 1.0f;      // stp3.py:218
+    }
+    // B: voxel rank of every point of this pixel's ray (bit-exact with the reference CPU path)
+    if (act) {
+      int* rrow = s_rank + wl * HP + h;
+      const float xw = inb ? __ldg(p.xs + w) : 0.f;
+      const float yh = s_ys[h];
+      for (int d = da; d < db; ++d) {
+        int rank = -1;
+        if (inb) {
+          const float dep = s_ds[d];
+          float x = __fmul_rn(xw, dep);                  // stp3.py:195: (u*d, v*d, d)
+          float y = __fmul_rn(yh, dep);
+          float z = dep;
+          affine_exact(s_mat, s_mat + 9, x, y, z);       // stp3.py:196-198
+          for (int k = 0; k < n_chain; ++k)              // stp3.py:270-277, sequential, rounded every step
+            affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
+          // stp3.py:287-289: ((p - (start - res/2)) / res).long() -- true division, truncation toward zero;
+          // trunc(q) in [0, n)  <=>  -1 < q < n  (keeps the (-1,0) band in cell 0 exactly like .long()).
+          const float qx = __fdiv_rn(__fsub_rn(x, offx), resx);
+          const float qy = __fdiv_rn(__fsub_rn(y, offy), resy);
+          const float qz = __fdiv_rn(__fsub_rn(z, offz), resz);
+          const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
+          if (keep) {
+            const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi
+            rank = ix * (p.ny * p.nz) + iy * p.nz + iz;              // stp3.py:251-255
+          }
+          if (p.ranks_out) p.ranks_out[(((size_t)img * D + d) * Hf + h) * Wf + w] = rank;
+        }
+        rrow[d * TW * HP] = rank;
+      }
     }
   }
   __syncthreads();
-  if (p.use_depth) {
-    // softmax over D (stp3.py:215): `parts` threads share one pixel, each owning a slice of the depth axis
-    const int npix_r = (npix + 31) & ~31;
-    const int parts = nthr / npix_r;
-    if (parts >= 1) {
-      const int pix = tid % npix_r, part = tid / npix_r;
-      const bool act = pix < npix && part < parts;
-      const int dchunk = (D + parts - 1) / parts;
-      const int da = part * dchunk, db = min(D, da + dchunk);
-      float mx = -INFINITY;
-      if (act) for (int d = da; d < db; ++d) mx = fmaxf(mx, __int_as_float(s_pt[d * npix + pix].y));
-      s_red[tid] = mx;
-      __syncthreads();
-      if (act) for (int q = 0; q < parts; ++q) mx = fmaxf(mx, s_red[q * npix_r + pix]);
-      __syncthreads();
-      float sum = 0.f;
-      if (act) for (int d = da; d < db; ++d) {
-        const float e = __expf(__int_as_float(s_pt[d * npix + pix].y) - mx);
-        s_pt[d * npix + pix].y = __float_as_int(e);
-        sum += e;
-      }
-      s_red[tid] = sum;
-      __syncthreads();
-      if (act) {
-        float tot = 0.f;
-        for (int q = 0; q < parts; ++q) tot += s_red[q * npix_r + pix];
-        const float inv = __frcp_rn(tot);
-        for (int d = da; d < db; ++d)
-          s_pt[d * npix + pix].y = __float_as_int(__int_as_float(s_pt[d * npix + pix].y) * inv);
-      }
-    } else {  // very tall tiles: one thread per pixel, several pixels per thread
-      for (int pix = tid; pix < npix; pix += nthr) {
-        float mx = -INFINITY;
-        for (int d = 0; d < D; ++d) mx = fmaxf(mx, __int_as_float(s_pt[d * npix + pix].y));
-        float sum = 0.f;
-        for (int d = 0; d < D; ++d) {
-          const float e = __expf(__int_as_float(s_pt[d * npix + pix].y) - mx);
-          s_pt[d * npix + pix].y = __float_as_int(e);
-          sum += e;
-        }
-        const float inv = __frcp_rn(sum);
-        for (int d = 0; d < D; ++d)
-          s_pt[d * npix + pix].y = __float_as_int(__int_as_float(s_pt[d * npix + pix].y) * inv);
-      }
-    }
-  } else {
-    for (int i = tid; i < npts; i += nthr) s_pt[i].y = __float_as_int(1.0f);  // stp3.py:218
-  }
-
-  // ---- phase B: voxel rank of every point of the tile (bit-exact with the reference CPU path)
-  {
-    const float offx = p.off[0], offy = p.off[1], offz = p.off[2];
-    const float resx = p.res[0], resy = p.res[1], resz = p.res[2];
-    const float fnx = (float)p.nx, fny = (float)p.ny, fnz = (float)p.nz;
-    for (int i = tid; i < npts; i += nthr) {
-      const int wl = i % TW;
-      const int dh = i / TW;
-      const int h = dh % Hf;
-      const int d = dh / Hf;
-      const int w = w0 + wl;
-      int rank = -1;
-      if (w < Wf) {
-        const float dep = s_ds[d];
-        float x = __fmul_rn(__ldg(p.xs + w), dep);     // stp3.py:195: (u*d, v*d, d)
-        float y = __fmul_rn(s_ys[h], dep);
-        float z = dep;
-        affine_exact(s_mat, s_mat + 9, x, y, z);       // stp3.py:196-198
-        for (int k = 0; k < n_chain; ++k)              // stp3.py:270-277, sequential, rounded every step
-          affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
-        // stp3.py:287-289: ((p - (start - res/2)) / res).long()  -- true division, truncation toward zero;
-        // trunc(q) in [0, n)  <=>  -1 < q < n  (this keeps the (-1,0) band in cell 0 exactly like .long()).
-        const float qx = __fdiv_rn(__fsub_rn(x, offx), resx);
-        const float qy = __fdiv_rn(__fsub_rn(y, offy), resy);
-        const float qz = __fdiv_rn(__fsub_rn(z, offz), resz);
-        const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
-        if (keep) {
-          const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi
-          rank = ix * (p.ny * p.nz) + iy * p.nz + iz;              // stp3.py:251-255
-        }
-        if (p.ranks_out) p.ranks_out[((size_t)img * D * Hf + dh) * Wf + w] = rank;
-      }
-      s_pt[i].x = rank;
-    }
+  // column summary: one thread per (d, wl)
+  for (int i = tid; i < D * TW; i += nthr) {
+    const int* r = s_rank + i * HP;
+    const int first = r[0];
+    bool uni = true;
+    for (int h = 1; h < Hf; ++h) uni &= (r[h] == first);
+    s_col[i] = uni ? first : -2;
   }
 
   // ---- phase C: outer product + segmented pooling.  work item = (column, depth slice); lanes = channel pairs
@@ -212,12 +237,11 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   unsigned char* obase = p.occ + (size_t)bt * nvox;
   const bool vec_ok = (C % 2) == 0;
   for (int c0 = 0; c0 < C; c0 += kCChunk) {
-    // stage the context features of channels [c0, c0+64) of this tile (stp3.py:216 reads them D times)
+    // stage the context features of channels [c0, c0+64) of this tile (stp3.py:216 re-reads them D times)
     __syncthreads();
     if (p.feat_nhwc) {
-      for (int i = tid; i < kCChunk * npix; i += nthr) {
-        const int cl = i % kCChunk;
-        const int px = i / kCChunk;              // h*TW + wl
+      for (int px = tid / kCChunk; px < npix; px += nthr / kCChunk) {
+        const int cl = tid % kCChunk;
         const int wl = px % TW, h = px / TW;
         const int w = w0 + wl, c = c0 + cl;
         float v = 0.f;
@@ -225,18 +249,23 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
         s_feat[feat_row(cl) * fstride + px] = v;
       }
     } else {
-      for (int i = tid; i < kCChunk * npix; i += nthr) {
-        const int px = i % npix;
-        const int cl = i / npix;
-        const int wl = px % TW, h = px / TW;
-        const int w = w0 + wl, c = c0 + cl;
-        float v = 0.f;
-        if (w < Wf && c < C) v = __ldg(p.feat + (((size_t)img * C + c) * Hf + h) * Wf + w);
-        s_feat[feat_row(cl) * fstride + px] = v;
+      for (int px0 = 0; px0 < npix; px0 += npix_r) {
+        const int px = px0 + tid % npix_r;
+        if (px < npix && my_part < parts) {
+          const int wl = px % TW, h = px / TW;
+          const int w = w0 + wl;
+          const float* src = p.feat + (((size_t)img * C + c0) * Hf + h) * Wf + w;
+          for (int cl = my_part; cl < kCChunk; cl += parts) {
+            float v = 0.f;
+            if (w < Wf && c0 + cl < C) v = __ldg(src + (size_t)cl * Hf * Wf);
+            s_feat[feat_row(cl) * fstride + px] = v;
+          }
+        }
       }
     }
     __syncthreads();
     const int c = c0 + 2 * lane;
+    const bool mark = (lane == 0) && (c0 == 0);
     for (int item = warp; item < TW * dsplit; item += nwarps) {
       const int wl = item % TW;
       if (w0 + wl >= Wf) continue;
@@ -253,38 +282,44 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
             f1[j] = s_feat[(lane + 32) * fstride + h * TW + wl];
           }
         }
-        int cur = -1;
-        float a0 = 0.f, a1 = 0.f;
         for (int d = d0; d < d1; ++d) {
-          const int2* row = s_pt + (size_t)(d * Hf + h0) * TW + wl;
+          const int col = s_col[d * TW + wl];
+          if (col == -1) continue;                   // the whole column is outside the grid
+          const float* pr = s_prob + (d * TW + wl) * HP + h0;
+          if (col >= 0) {
+            // fast path: the column is one segment -> 8 FFMA per broadcast LDS.128, one flush
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < kHChunk; ++j) {
-            if (h0 + j < Hf) {
-              const int2 v = row[j * TW];
-              if (v.x != cur) {                      // warp-uniform: segment boundary
-                if (cur >= 0) {
-                  if (c < C) {
-                    float* dst = gbase + (size_t)cur * C + c;
-                    if (vec_ok) red_add_v2(dst, a0, a1);
-                    else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
-                  }
-                  if (lane == 0 && c0 == 0) obase[cur] = 1;
-                }
-                cur = v.x; a0 = 0.f; a1 = 0.f;
+            for (int j4 = 0; j4 < kHChunk / 4; ++j4) {
+              if (h0 + 4 * j4 < Hf) {
+                const float4 q = *reinterpret_cast<const float4*>(pr + 4 * j4);
+                a0 = fmaf(q.x, f0[4 * j4 + 0], a0); a1 = fmaf(q.x, f1[4 * j4 + 0], a1);
+                a0 = fmaf(q.y, f0[4 * j4 + 1], a0); a1 = fmaf(q.y, f1[4 * j4 + 1], a1);
+                a0 = fmaf(q.z, f0[4 * j4 + 2], a0); a1 = fmaf(q.z, f1[4 * j4 + 2], a1);
+                a0 = fmaf(q.w, f0[4 * j4 + 3], a0); a1 = fmaf(q.w, f1[4 * j4 + 3], a1);
               }
-              const float pr = __int_as_float(v.y);
-              a0 = fmaf(pr, f0[j], a0);
-              a1 = fmaf(pr, f1[j], a1);
             }
+            flush_segment(gbase, obase, col, C, c, vec_ok, mark, a0, a1);
+          } else {
+            // slow path: segmented reduction over equal ranks along the column
+            const int* rk = s_rank + (d * TW + wl) * HP + h0;
+            int cur = -1;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kHChunk; ++j) {
+              if (h0 + j < Hf) {
+                const int r = rk[j];
+                if (r != cur) {                      // warp-uniform: segment boundary
+                  if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
+                  cur = r; a0 = 0.f; a1 = 0.f;
+                }
+                const float q = pr[j];
+                a0 = fmaf(q, f0[j], a0);
+                a1 = fmaf(q, f1[j], a1);
+              }
+            }
+            if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
           }
-        }
-        if (cur >= 0) {
-          if (c < C) {
-            float* dst = gbase + (size_t)cur * C + c;
-            if (vec_ok) red_add_v2(dst, a0, a1);
-            else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
-          }
-          if (lane == 0 && c0 == 0) obase[cur] = 1;
         }
       }
     }
@@ -292,74 +327,81 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 }
 
 // out[b,t] = out[b,t-1]*discount + grid[b,t]  (stp3.py:296, separate fp32 mul and add like the reference's
-// `bev_feature * discount + tmp`), written either channels-last or as (C, X*Y) through a 32x32 shared-memory
-// transpose.  One CTA = 32 consecutive pillars of one sample, all channels, all frames.  Only occupied
-// (frame, pillar) rows of the grid are read; they are zeroed again and their occupancy byte cleared, which
-// leaves the workspace clean for the next call.  pool_sum (B,S,C) += sum over cells (optional).
-__global__ void __launch_bounds__(256)
+// `bev_feature * discount + tmp`).  One CTA = 32 consecutive pillars of one sample; lane = pillar, warp = a group
+// of 8 channels, so every global store of the (C, X*Y) output is a fully coalesced 128-byte row segment and no
+// shared memory or barrier is needed.  Only occupied (frame, pillar) rows of the scatter grid are read; they are
+// zeroed again and their occupancy byte cleared, which leaves the workspace clean for the next call.
+// pool_sum (B,S,C) += sum over cells (optional).
+template <bool VEC>
+__global__ void __launch_bounds__(1024)
 bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, float* __restrict__ out,
                     float* __restrict__ pool_sum, int S, int C, int nvox, float discount, int out_nhwc) {
-  __shared__ float tile[32][33];
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;     // (32, 8); warp == ty
-  // occupancy bits of this warp's 4 pillars for every frame: bit (t*4 + k)
+  const int lane = threadIdx.x;
+  const int pcell = blockIdx.x * 32 + lane;
+  const int c0 = threadIdx.y * 8;
+  const bool valid = pcell < nvox;
+  // every warp reads the occupancy of its 32 pillars for all frames first (independent loads)
   unsigned occ_bits = 0;
+  for (int t = 0; t < S; ++t)
+    if (valid && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << t;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (int t = 0; t < S; ++t) {
+    const size_t bt = (size_t)b * S + t;
+    float v[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int pcell = p0 + ty + 8 * k;
-      if (pcell < nvox && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << (t * 4 + k);
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (occ_bits & (1u << t)) {
+      float* src = grid + (bt * nvox + pcell) * C + c0;
+      if (VEC) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 lo = *reinterpret_cast<const float4*>(src);
+        const float4 hi = *reinterpret_cast<const float4*>(src + 4);
+        *reinterpret_cast<float4*>(src) = z;
+        *reinterpret_cast<float4*>(src + 4) = z;
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c0 + i < C) { v[i] = src[i]; src[i] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(__fmul_rn(acc[i], discount), v[i]);
+    if (valid) {
+      if (out_nhwc) {
+        float* dst = out + (bt * nvox + pcell) * C + c0;
+        if (VEC) {
+          __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
+          __stcs(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (c0 + i < C) dst[i] = acc[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (VEC || c0 + i < C) __stcs(out + (bt * C + c0 + i) * (size_t)nvox + pcell, acc[i]);
+      }
+    }
+    if (pool_sum) {                      // per-(b,t,c) spatial sum for the pyramid-pooling branch
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && c0 + i < C) atomicAdd(pool_sum + bt * C + c0 + i, s);
+      }
     }
   }
-  __syncwarp();
-  if (tx == 0) {
+  // all warps of the CTA have read the occupancy bytes of these 32 pillars before they are cleared
+  __syncthreads();
+  if (threadIdx.y == 0)
     for (int t = 0; t < S; ++t)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (occ_bits & (1u << (t * 4 + k))) occ[((size_t)b * S + t) * nvox + p0 + ty + 8 * k] = 0;
-  }
-  const bool use_tile = !out_nhwc || pool_sum != nullptr;
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int c = c0 + tx;
-    for (int t = 0; t < S; ++t) {
-      const size_t bt = (size_t)b * S + t;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int pl = ty + 8 * k;                      // pillar within tile
-        const int pcell = p0 + pl;
-        float v = 0.f;
-        if ((occ_bits & (1u << (t * 4 + k))) && c < C) {
-          float* src = grid + (bt * nvox + pcell) * C + c;
-          v = *src;
-          *src = 0.f;
-        }
-        acc[k] = __fadd_rn(__fmul_rn(acc[k], discount), v);   // out-of-range entries stay exactly zero
-        if (out_nhwc && pcell < nvox && c < C) out[(bt * nvox + pcell) * C + c] = acc[k];
-        if (use_tile) tile[pl][tx] = acc[k];
-      }
-      if (use_tile) {
-        __syncthreads();
-        if (!out_nhwc) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int cl = ty + 8 * k;
-            const int cc = c0 + cl, pcell = p0 + tx;
-            if (cc < C && pcell < nvox) __stcs(out + (bt * C + cc) * (size_t)nvox + pcell, tile[tx][cl]);
-          }
-        }
-        if (pool_sum && ty == 0 && c < C) {       // per-(b,t,c) spatial sum for the pyramid-pooling branch
-          float tot = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) tot += tile[r][tx];
-          atomicAdd(pool_sum + bt * C + c, tot);
-        }
-        __syncthreads();
-      }
-    }
-  }
+      if (occ_bits & (1u << t)) occ[((size_t)b * S + t) * nvox + pcell] = 0;
 }
+
 
 }  // namespace stp3
 
@@ -421,8 +463,8 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   // tile width: as wide as shared memory allows (<= 4 columns), at least 1
   int TW = 4;
   auto smem_for = [&](int tw) {
-    const int npix = Hf * tw;
-    return (size_t)D * npix * sizeof(int2) +
+    const int npix = Hf * tw, HP = (Hf + 3) & ~3;
+    return (size_t)D * tw * HP * 8 + (size_t)D * tw * 4 +
            (size_t)(kCChunk * (npix | 1) + 12 * kMaxFrames + Hf + D + kScatterThreads) * sizeof(float);
   };
   while (TW > 1 && smem_for(TW) > 110 * 1024) TW >>= 1;
@@ -430,17 +472,25 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   STP3_CHECK_ARG(smem <= 227 * 1024, "D*Hf = %d too large for one image column in shared memory", D * Hf);
   p.TW = TW;
   p.tiles_w = ceil_div(Wf, TW);
-
-  STP3_CUDA_OK(cudaFuncSetAttribute(lift_splat_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nblk = (long long)B * S * N * p.tiles_w;
   STP3_CHECK_ARG(nblk < (1ll << 31), "grid too large");
-  lift_splat_scatter_kernel<<<(unsigned)nblk, kScatterThreads, smem, stream>>>(p);
-  STP3_CUDA_OK(cudaGetLastError());
+  auto launch = [&](auto kernel) -> int {
+    STP3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)nblk, kScatterThreads, smem, stream>>>(p);
+    STP3_CUDA_OK(cudaGetLastError());
+    return STP3_OK;
+  };
+  int rc = TW == 4 ? launch(lift_splat_scatter_kernel<4>)
+         : TW == 2 ? launch(lift_splat_scatter_kernel<2>) : launch(lift_splat_scatter_kernel<1>);
+  if (rc != STP3_OK) return rc;
 
   const int nvox = nx * ny * nz;
-  STP3_CHECK_ARG(S * 4 <= 32, "S too large for the finalize occupancy mask");
-  dim3 fgrid(ceil_div(nvox, 32), B), fblock(32, 8);
-  bev_finalize_kernel<<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
+  STP3_CHECK_ARG(C <= 256, "C=%d: the finalize kernel supports up to 256 channels", C);
+  dim3 fgrid(ceil_div(nvox, 32), B), fblock(32, ceil_div(C, 8));
+  if (C % 8 == 0)
+    bev_finalize_kernel<true><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
+  else
+    bev_finalize_kernel<false><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }
