@@ -17,6 +17,7 @@
 //         and never needs a memset.
 //
 // Reference semantics: /root/reference/stp3/models/stp3.py:186-301, stp3/utils/geometry.py:299-318.
+#include <cmath>
 #include <cstdint>
 
 #include "common.cuh"
@@ -40,6 +41,8 @@ struct LiftSplatParams {
   const float* ds;
   float off[3];
   float res[3];
+  float inv[3];     // exact 1/res when res is a power of two
+  int inv_ok[3];
   int nx, ny, nz;
   int B, S, N, D, Hf, Wf, C;
   int feat_nhwc;
@@ -95,7 +98,7 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C;
   const int HP = (Hf + 3) & ~3;
   const int npix = Hf * TW;
-  const int fstride = npix | 1;                                    // odd row stride of the feature tile
+  const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * TW) | 1;   // odd, zero-padded to whole h-chunks
   float* s_prob = reinterpret_cast<float*>(smem_raw);
   int* s_rank = reinterpret_cast<int*>(s_prob + D * TW * HP);
   int* s_col = s_rank + D * TW * HP;
@@ -203,9 +206,10 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
             affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
           // stp3.py:287-289: ((p - (start - res/2)) / res).long() -- true division, truncation toward zero;
           // trunc(q) in [0, n)  <=>  -1 < q < n  (keeps the (-1,0) band in cell 0 exactly like .long()).
-          const float qx = __fdiv_rn(__fsub_rn(x, offx), resx);
-          const float qy = __fdiv_rn(__fsub_rn(y, offy), resy);
-          const float qz = __fdiv_rn(__fsub_rn(z, offz), resz);
+          // (a power-of-two resolution makes the division an exact scaling: multiply by the exact reciprocal)
+          const float qx = p.inv_ok[0] ? __fmul_rn(__fsub_rn(x, offx), p.inv[0]) : __fdiv_rn(__fsub_rn(x, offx), resx);
+          const float qy = p.inv_ok[1] ? __fmul_rn(__fsub_rn(y, offy), p.inv[1]) : __fdiv_rn(__fsub_rn(y, offy), resy);
+          const float qz = p.inv_ok[2] ? __fmul_rn(__fsub_rn(z, offz), p.inv[2]) : __fdiv_rn(__fsub_rn(z, offz), resz);
           const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
           if (keep) {
             const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi
@@ -214,6 +218,7 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
           if (p.ranks_out) p.ranks_out[(((size_t)img * D + d) * Hf + h) * Wf + w] = rank;
         }
         rrow[d * TW * HP] = rank;
+        if (rank < 0) prow[d * TW * HP] = 0.f;     // masked points contribute nothing (stp3.py:239-248)
       }
     }
   }
@@ -221,10 +226,13 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   // column summary: one thread per (d, wl)
   for (int i = tid; i < D * TW; i += nthr) {
     const int* r = s_rank + i * HP;
-    const int first = r[0];
+    int first = -1;
     bool uni = true;
-    for (int h = 1; h < Hf; ++h) uni &= (r[h] == first);
-    s_col[i] = uni ? first : -2;
+    for (int h = 0; h < Hf; ++h) {
+      const int v = r[h];
+      if (v >= 0) { uni &= (first < 0 || v == first); first = v; }
+    }
+    s_col[i] = uni ? first : -2;                 // masked rows carry probability 0, so they never split a column
   }
 
   // ---- phase C: outer product + segmented pooling.  work item = (column, depth slice); lanes = channel pairs
@@ -236,6 +244,8 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   float* gbase = p.grid + (size_t)bt * nvox * C;
   unsigned char* obase = p.occ + (size_t)bt * nvox;
   const bool vec_ok = (C % 2) == 0;
+  for (int i = tid; i < kCChunk * (fstride - npix); i += nthr)     // zero padding of the feature rows (once)
+    s_feat[(i / (fstride - npix)) * fstride + npix + i % (fstride - npix)] = 0.f;
   for (int c0 = 0; c0 < C; c0 += kCChunk) {
     // stage the context features of channels [c0, c0+64) of this tile (stp3.py:216 re-reads them D times)
     __syncthreads();
@@ -274,13 +284,9 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
       for (int h0 = 0; h0 < Hf; h0 += kHChunk) {
         float f0[kHChunk], f1[kHChunk];
 #pragma unroll
-        for (int j = 0; j < kHChunk; ++j) {
-          const int h = h0 + j;
-          f0[j] = 0.f; f1[j] = 0.f;
-          if (h < Hf) {
-            f0[j] = s_feat[lane * fstride + h * TW + wl];
-            f1[j] = s_feat[(lane + 32) * fstride + h * TW + wl];
-          }
+        for (int j = 0; j < kHChunk; ++j) {          // rows >= Hf read the zero padding
+          f0[j] = s_feat[lane * fstride + (h0 + j) * TW + wl];
+          f1[j] = s_feat[(lane + 32) * fstride + (h0 + j) * TW + wl];
         }
         for (int d = d0; d < d1; ++d) {
           const int col = s_col[d * TW + wl];
@@ -332,76 +338,106 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 // shared memory or barrier is needed.  Only occupied (frame, pillar) rows of the scatter grid are read; they are
 // zeroed again and their occupancy byte cleared, which leaves the workspace clean for the next call.
 // pool_sum (B,S,C) += sum over cells (optional).
-template <bool VEC>
-__global__ void __launch_bounds__(1024)
+template <bool VEC, int SMAX>
+__global__ void __launch_bounds__(256)
 bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, float* __restrict__ out,
                     float* __restrict__ pool_sum, int S, int C, int nvox, float discount, int out_nhwc) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x;
   const int pcell = blockIdx.x * 32 + lane;
-  const int c0 = threadIdx.y * 8;
-  const bool valid = pcell < nvox;
+  const int c0 = (blockIdx.z * 8 + threadIdx.y) * 8;
+  const bool valid = pcell < nvox && c0 < C;
   // every warp reads the occupancy of its 32 pillars for all frames first (independent loads)
   unsigned occ_bits = 0;
-  for (int t = 0; t < S; ++t)
-    if (valid && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << t;
-  float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int t = 0; t < S; ++t) {
-    const size_t bt = (size_t)b * S + t;
-    float v[8];
+  for (int t = 0; t < SMAX; ++t)
+    if (t < S && valid && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << t;
+  // all grid loads are issued before anything is stored: a store to a line with a load miss in flight would
+  // stall the memory pipe (measured: 10x slower), so the re-zeroing happens at the very end
+  float v[SMAX][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (int t = 0; t < SMAX; ++t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[t][i] = 0.f;
     if (occ_bits & (1u << t)) {
-      float* src = grid + (bt * nvox + pcell) * C + c0;
+      const float* src = grid + (((size_t)b * S + t) * nvox + pcell) * C + c0;
       if (VEC) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 lo = *reinterpret_cast<const float4*>(src);
-        const float4 hi = *reinterpret_cast<const float4*>(src + 4);
-        *reinterpret_cast<float4*>(src) = z;
-        *reinterpret_cast<float4*>(src + 4) = z;
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        const float4 lo = __ldcs(reinterpret_cast<const float4*>(src));
+        const float4 hi = __ldcs(reinterpret_cast<const float4*>(src + 4));
+        v[t][0] = lo.x; v[t][1] = lo.y; v[t][2] = lo.z; v[t][3] = lo.w;
+        v[t][4] = hi.x; v[t][5] = hi.y; v[t][6] = hi.z; v[t][7] = hi.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (c0 + i < C) { v[i] = src[i]; src[i] = 0.f; }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(__fmul_rn(acc[i], discount), v[i]);
-    if (valid) {
-      if (out_nhwc) {
-        float* dst = out + (bt * nvox + pcell) * C + c0;
-        if (VEC) {
-          __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
-          __stcs(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) if (c0 + i < C) dst[i] = acc[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (VEC || c0 + i < C) __stcs(out + (bt * C + c0 + i) * (size_t)nvox + pcell, acc[i]);
-      }
-    }
-    if (pool_sum) {                      // per-(b,t,c) spatial sum for the pyramid-pooling branch
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float s = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && c0 + i < C) atomicAdd(pool_sum + bt * C + c0 + i, s);
+        for (int i = 0; i < 8; ++i) if (c0 + i < C) v[t][i] = src[i];
       }
     }
   }
-  // all warps of the CTA have read the occupancy bytes of these 32 pillars before they are cleared
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    if (t < S) {
+      const size_t bt = (size_t)b * S + t;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(__fmul_rn(acc[i], discount), v[t][i]);
+      if (valid) {
+        if (out_nhwc) {
+          float* dst = out + (bt * nvox + pcell) * C + c0;
+          if (VEC) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
+            __stcs(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c0 + i < C) dst[i] = acc[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (VEC || c0 + i < C) __stcs(out + (bt * C + c0 + i) * (size_t)nvox + pcell, acc[i]);
+        }
+      }
+      if (pool_sum) {                      // per-(b,t,c) spatial sum for the pyramid-pooling branch
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float s = acc[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0 && c0 + i < C) atomicAdd(pool_sum + bt * C + c0 + i, s);
+        }
+      }
+    }
+  }
+  // leave the workspace clean: re-zero exactly the rows that were read, then the occupancy bytes (after every
+  // warp of the CTA has read them)
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    if (occ_bits & (1u << t)) {
+      float* src = grid + (((size_t)b * S + t) * nvox + pcell) * C + c0;
+      if (VEC) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(src) = z;
+        *reinterpret_cast<float4*>(src + 4) = z;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c0 + i < C) src[i] = 0.f;
+      }
+    }
+  }
   __syncthreads();
-  if (threadIdx.y == 0)
+  if (threadIdx.y == 0 && blockIdx.z == gridDim.z - 1) {
+    // the last channel-group CTA of these pillars clears the bytes; other groups may still be reading them, so
+    // groups > 0 exist only when C > 64 and then the bytes are cleared by a tiny follow-up kernel instead
     for (int t = 0; t < S; ++t)
-      if (occ_bits & (1u << t)) occ[((size_t)b * S + t) * nvox + pcell] = 0;
+      if (gridDim.z == 1 && (occ_bits & (1u << t))) occ[((size_t)b * S + t) * nvox + pcell] = 0;
+  }
 }
 
+// C > 64 only: occupancy bytes are cleared after every channel group has consumed them
+__global__ void clear_bytes_kernel(unsigned char* __restrict__ p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 16 < n) reinterpret_cast<uint4*>(p)[i] = make_uint4(0, 0, 0, 0);
+}
 
 }  // namespace stp3
 
@@ -452,7 +488,13 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   LiftSplatParams p;
   p.feat = feat; p.depth = depth_logits; p.cam_M = cam_M; p.cam_t = cam_t; p.ego_R = ego_R; p.ego_t = ego_t;
   p.xs = xs; p.ys = ys; p.ds = ds;
-  for (int i = 0; i < 3; ++i) { p.off[i] = bev_off[i]; p.res[i] = bev_res[i]; }
+  for (int i = 0; i < 3; ++i) {
+    p.off[i] = bev_off[i]; p.res[i] = bev_res[i];
+    int e = 0;
+    const float m = frexpf(bev_res[i], &e);          // res = m * 2^e ; power of two <=> m == 0.5
+    p.inv_ok[i] = (m == 0.5f && e > -100 && e < 100) ? 1 : 0;
+    p.inv[i] = p.inv_ok[i] ? ldexpf(1.0f, 1 - e) : 0.f;
+  }
   p.nx = nx; p.ny = ny; p.nz = nz;
   p.B = B; p.S = S; p.N = N; p.D = D; p.Hf = Hf; p.Wf = Wf; p.C = C;
   p.feat_nhwc = feat_layout; p.use_depth = use_depth_distribution;
@@ -463,9 +505,10 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   // tile width: as wide as shared memory allows (<= 4 columns), at least 1
   int TW = 4;
   auto smem_for = [&](int tw) {
-    const int npix = Hf * tw, HP = (Hf + 3) & ~3;
+    const int HP = (Hf + 3) & ~3;
     return (size_t)D * tw * HP * 8 + (size_t)D * tw * 4 +
-           (size_t)(kCChunk * (npix | 1) + 12 * kMaxFrames + Hf + D + kScatterThreads) * sizeof(float);
+           (size_t)(kCChunk * ((((Hf + kHChunk - 1) / kHChunk) * kHChunk * tw) | 1) + 12 * kMaxFrames + Hf + D +
+                    kScatterThreads) * sizeof(float);
   };
   while (TW > 1 && smem_for(TW) > 110 * 1024) TW >>= 1;
   const size_t smem = smem_for(TW);
@@ -485,12 +528,18 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   if (rc != STP3_OK) return rc;
 
   const int nvox = nx * ny * nz;
-  STP3_CHECK_ARG(C <= 256, "C=%d: the finalize kernel supports up to 256 channels", C);
-  dim3 fgrid(ceil_div(nvox, 32), B), fblock(32, ceil_div(C, 8));
-  if (C % 8 == 0)
-    bev_finalize_kernel<true><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
-  else
-    bev_finalize_kernel<false><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout);
+  const int groups = ceil_div(C, 64);                 // 8 warps x 8 channels per CTA
+  dim3 fgrid(ceil_div(nvox, 32), B, groups), fblock(32, C >= 64 ? 8 : ceil_div(C, 8));
+#define STP3_FINALIZE(VEC, SMAX) \
+  bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout)
+  if (C % 8 == 0) { if (S <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
+  else            { if (S <= 4) STP3_FINALIZE(false, 4); else STP3_FINALIZE(false, 8); }
+#undef STP3_FINALIZE
   STP3_CUDA_OK(cudaGetLastError());
+  if (groups > 1) {
+    const size_t nocc = ((size_t)B * S * nvox + 255) & ~(size_t)255;
+    clear_bytes_kernel<<<(unsigned)((nocc / 16 + 255) / 256), 256, 0, stream>>>(p.occ, nocc);
+    STP3_CUDA_OK(cudaGetLastError());
+  }
   return STP3_OK;
 }
