@@ -82,6 +82,48 @@ int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_l
                         void* workspace, size_t workspace_bytes,
                         float* out, int out_layout, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense layers: implicit-GEMM convolution on tcgen05 tensor cores (TMEM accumulators, TMA-fed operands).
+ *
+ * One entry point covers every convolution of the temporal block, the per-frame DeepLab head and the BEV decoder:
+ *   CausalConv3d / conv_1x1x1_norm_activated / TemporalBlock   stp3/layers/temporal.py:252-273, 315-325, 426-489
+ *   ASPP / DeepLabHead / UpsamplingAdd / UpsamplingConcat      stp3/layers/convolutions.py:183-280
+ *   Decoder (ResNet-18 stages + heads)                         stp3/models/decoder.py:8-140
+ * Eval-mode BatchNorm is folded into w / bias by the caller (stp3_b200/dense.py); ReLU, residual add, per-image
+ * bias (the spatially constant pyramid-pool / ASPP-pool / ego-motion branches) and the concat offset are fused.
+ *
+ * Activations are channels-last and carried as TWO bf16 planes (hi = bf16(x), lo = bf16(x - hi)) so that the bf16
+ * tensor pipe reproduces fp32 convolution to ~1e-5 (three MMAs per product: hi*hi + hi*lo + lo*hi):
+ *   x_hi, x_lo   (B, T, H, W, in_cstride) bf16, in_cstride % 64 == 0, padding channels zero
+ *   w            [ntaps][cin/64][2 planes][bn][64] bf16: tap-major, K-major rows of 64 input channels
+ *   bias         [bn] fp32;  img_bias  optional [B*T][bn] fp32
+ *   res_hi/lo    optional residual (B*T, Ho, Wo, res_cstride), channels [res_coff, res_coff+bn)
+ *   y_hi, y_lo   optional output planes (B*T, Ho, Wo, out_cstride), channels [out_coff, out_coff+bn)
+ *   y_f32        optional (B*T, n_valid, Ho, Wo) fp32 in the reference's NCHW layout (final logits)
+ * taps[i] = (dt, dy, dx): input coordinate = output coordinate * stride + d (dt is not strided); coordinates
+ * outside the tensor read as zero (this is the reference's zero / causal padding).
+ */
+typedef struct stp3_conv_desc {
+  int B, T, H, W;        /* input: B samples x T frames of H x W pixels */
+  int in_cstride;        /* channels of the input tensor */
+  int cin_off, cin;      /* channel window this convolution reads (multiples of 64) */
+  int Ho, Wo;            /* output spatial size */
+  int stride;            /* spatial stride, 1 or 2 */
+  int ntaps;             /* 1 .. 49 */
+  signed char taps[49][3];
+  int bn;                /* padded output channels: 64, 128 or 256 */
+  int out_cstride, out_coff;
+  int relu;              /* apply ReLU */
+  int res_mode;          /* 0 none, 1 residual added before the activation, 2 after it */
+  int res_cstride, res_coff;
+  int n_valid;           /* real output channels written to y_f32 */
+  int sigmoid;           /* apply a sigmoid to y_f32 (instance_center head, decoder.py:70) */
+} stp3_conv_desc;
+
+int stp3_conv_fwd(const stp3_conv_desc* desc, const void* x_hi, const void* x_lo, const void* w, const float* bias,
+                  const float* img_bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
+                  float* y_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

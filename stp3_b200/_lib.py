@@ -19,12 +19,21 @@ _I = ctypes.c_int
 _F = ctypes.c_float
 _SZ = ctypes.c_size_t
 _FP = ctypes.POINTER(ctypes.c_float)
+class ConvDesc(ctypes.Structure):
+    """Mirror of stp3_conv_desc (include/stp3_b200.h)."""
+    _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("in_cstride", _I), ("cin_off", _I), ("cin", _I),
+                ("Ho", _I), ("Wo", _I), ("stride", _I), ("ntaps", _I), ("taps", (ctypes.c_byte * 3) * 49),
+                ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("relu", _I), ("res_mode", _I),
+                ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I)]
+
+
 SIGNATURES = {
     "stp3_abi_version": (_I, []),
     "stp3_build_info": (ctypes.c_char_p, []),
     "stp3_last_error": (ctypes.c_char_p, []),
     "stp3_lift_splat_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "stp3_lift_splat_workspace_init": (_I, [_V, _SZ, _V]),
+    "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
                                  _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,
                                  _V, _V, _V, _SZ, _V, _I, _V]),

@@ -1,0 +1,327 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// One kernel family covers every dense layer of the hot path (1x1x1, causal (2,3,3) / (1,3,3) 3-D, dilated 3x3,
+// 7x7 stride 2, 3x3 / 1x1 stride 2): a convolution is a sum over taps of [pixels x Cin] . [Cin x Cout] GEMMs whose
+// A operand is a shifted (strided, zero-padded) window of the channels-last activation tensor -- exactly what a
+// 5-D TMA box with out-of-bounds zero fill delivers.
+//
+// Precision: fp32 tensors are carried as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); every product is
+// evaluated as hi*hi + hi*lo + lo*hi on the bf16 tensor pipe with fp32 accumulation in TMEM (error ~2^-16 per
+// product instead of 2^-8), which keeps 25 stacked layers inside the 1e-3 parity bar.  Eval-mode BatchNorm is
+// folded into the weights/bias on the host; bias, per-image bias (pyramid-pool / ASPP-pool / ego-motion
+// branches), ReLU, residual add and the concat offset are fused in the epilogue.
+//
+//   CTA tile : 128 output pixels (8 rows x 16 columns of one image) x BN output channels (64 / 128 / 256)
+//   K loop   : taps x (Cin / 64); per step TMA brings A_hi, A_lo (128x64 bf16, 128B-swizzled) and B_hi, B_lo
+//              (BN x 64) and one thread issues 4 (UMMA_K=16) x 3 tcgen05.mma
+//   warps    : 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM -> regs -> global)
+//
+// Reference layers: stp3/layers/temporal.py:252-489, stp3/layers/convolutions.py:183-280, stp3/models/decoder.py.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace stp3 {
+
+constexpr int kConvThreads = 192;
+constexpr int kTileH = 8, kTileW = 16;          // 128 output pixels = UMMA M
+constexpr int kBK = 64;                         // channels per K step (one 128-byte swizzle row of bf16)
+constexpr int kMaxTaps = 49;
+
+struct ConvParams {
+  int n_img, T, Ho, Wo;
+  int tiles_x, tiles_y;
+  int stride;
+  int kblocks;              // Cin / 64 of this convolution
+  int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
+  int ntaps;
+  signed char tap[kMaxTaps][4];   // (dt, dy, dx): input coordinate = output coordinate * stride + d
+  const float* bias;        // [BN]
+  const float* img_bias;    // [n_img][BN] or null
+  int relu;
+  int res_mode;             // 0 none, 1 residual added before the activation, 2 after
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  int res_cstride, res_coff;
+  __nv_bfloat16* out_hi;    // channels-last (n_img, Ho, Wo, out_cstride), may be null when out_f32 is used
+  __nv_bfloat16* out_lo;
+  int out_cstride, out_coff;
+  float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
+  int n_valid;
+  int sigmoid;              // apply to out_f32 (instance_center head)
+};
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int kStageBytes = 2 * 128 * kBK * 2 + 2 * BN * kBK * 2;
+  static constexpr int kStages = (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr size_t kBytes = 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + 2 * BN * sizeof(float) + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
+  using S = ConvSmem<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* stage_base = smem;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S::kStages * S::kStageBytes);   // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * BN);
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + S::kStages;        // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+  const int img = tile;
+  const int bidx = img / p.T, tidx = img % p.T;
+  const int ox0 = tx * kTileW, oy0 = ty * kTileH;
+  const int k_iters = p.ntaps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
+    for (int i = 0; i < S::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+    s_bias[i] = p.bias[i];
+    s_bias[BN + i] = p.img_bias ? p.img_bias[(size_t)img * BN + i] : 0.f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int tap = it / p.kblocks, kb = it % p.kblocks;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        unsigned char* sa_hi = stage_base + (size_t)stage * S::kStageBytes;
+        unsigned char* sa_lo = sa_hi + 128 * kBK * 2;
+        unsigned char* sb_hi = sa_lo + 128 * kBK * 2;
+        unsigned char* sb_lo = sb_hi + BN * kBK * 2;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+        const int c = p.cin_off + kb * kBK;
+        const int x = ox0 * p.stride + p.tap[tap][2];
+        const int y = oy0 * p.stride + p.tap[tap][1];
+        const int t = tidx + p.tap[tap][0];
+        ptx::tma_load_5d(sa_hi, &tm_a_hi, &full_bar[stage], c, x, y, t, bidx);
+        ptx::tma_load_5d(sa_lo, &tm_a_lo, &full_bar[stage], c, x, y, t, bidx);
+        const int wrow = (it * 2) * BN;            // [tap][kb][plane][BN] rows of 64
+        ptx::tma_load_2d(sb_hi, &tm_w, &full_bar[stage], 0, wrow);
+        ptx::tma_load_2d(sb_lo, &tm_w, &full_bar[stage], 0, wrow + BN);
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)stage * S::kStageBytes);
+        const uint32_t a_lo = a_hi + 128 * kBK * 2;
+        const uint32_t b_hi = a_lo + 128 * kBK * 2;
+        const uint32_t b_lo = b_hi + BN * kBK * 2;
+        const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_lo);
+        const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_lo);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
+          ptx::umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
+          ptx::umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1);
+          ptx::umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, 1);
+        }
+        ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
+        if (it == k_iters - 1) ptx::umma_commit(tmem_full_bar);
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                 // row of the tile = output pixel
+    const int oy = oy0 + (r >> 4), ox = ox0 + (r & 15);
+    const bool valid = oy < p.Ho && ox < p.Wo;
+    const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t acc[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, acc);
+      ptx::tmem_ld_wait();
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[j * 32 + i] + s_bias[BN + j * 32 + i];
+        if (p.res_mode) {
+          const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + j * 32);
+          const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + j * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float r0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+              const float r1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+              float& a0 = v[g * 8 + e * 2], &a1 = v[g * 8 + e * 2 + 1];
+              if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
+              else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+            }
+          }
+        } else if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.out_hi) {
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + j * 32);
+          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + j * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+        if (p.out_f32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = j * 32 + i;
+            if (c < p.n_valid) {
+              float x = v[i];
+              if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
+              p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace stp3
+
+using namespace stp3;
+
+extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w,
+                             const float* bias, const float* img_bias, const void* res_hi, const void* res_lo,
+                             void* y_hi, void* y_lo, float* y_f32, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STP3_CHECK_ARG(d && x_hi && x_lo && w && bias, "stp3_conv_fwd: null pointer argument");
+  STP3_CHECK_ARG((y_hi && y_lo) || y_f32, "stp3_conv_fwd: no output tensor");
+  STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "non-positive dimension");
+  STP3_CHECK_ARG(d->in_cstride % 64 == 0 && d->cin % 64 == 0 && d->cin_off % 64 == 0 && d->cin > 0 &&
+                 d->cin_off + d->cin <= d->in_cstride, "input channels must be padded to multiples of 64");
+  STP3_CHECK_ARG(d->bn == 64 || d->bn == 128 || d->bn == 256, "bn (padded output channels) must be 64, 128 or 256");
+  STP3_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+  STP3_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "ntaps out of range");
+  if (y_hi) STP3_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->bn <= d->out_cstride,
+                           "output channel window does not fit the output tensor");
+  if (d->res_mode) STP3_CHECK_ARG(res_hi && res_lo && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 &&
+                                  d->res_coff + d->bn <= d->res_cstride, "bad residual tensor");
+  if (y_f32) STP3_CHECK_ARG(d->n_valid > 0 && d->n_valid <= d->bn, "n_valid out of range");
+  PFN_tmapEncodeTiled enc = encode_fn();
+  if (!enc) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)d->in_cstride, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->T,
+                                (cuuint64_t)d->B};
+    const cuuint64_t strides[4] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
+                                   (cuuint64_t)d->H * d->W * d->in_cstride * 2,
+                                   (cuuint64_t)d->T * d->H * d->W * d->in_cstride * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)((kTileW - 1) * d->stride + 1),
+                               (cuuint32_t)((kTileH - 1) * d->stride + 1), 1, 1};
+    const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+    CUresult r1 = enc(&tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_hi), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_lo), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+      return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d %d", (int)r1, (int)r2);
+  }
+  const int kblocks = d->cin / kBK;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)kBK, (cuuint64_t)d->ntaps * kblocks * 2 * d->bn};
+    const cuuint64_t strides[1] = {(cuuint64_t)kBK * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)d->bn};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+
+  ConvParams p;
+  p.n_img = d->B * d->T; p.T = d->T; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, kTileH);
+  p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
+  for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
+  p.bias = bias; p.img_bias = img_bias; p.relu = d->relu; p.res_mode = d->res_mode;
+  p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
+  p.res_cstride = d->res_cstride; p.res_coff = d->res_coff;
+  p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
+  p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+  p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
+
+  const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;
+  STP3_CHECK_ARG(nblk > 0 && nblk < (1ll << 31), "grid too large");
+#define STP3_LAUNCH_CONV(BN_)                                                                                     \
+  do {                                                                                                            \
+    STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)ConvSmem<BN_>::kBytes));                                               \
+    conv_igemm_kernel<BN_><<<(unsigned)nblk, kConvThreads, ConvSmem<BN_>::kBytes, stream>>>(tm_hi, tm_lo, tm_w, p); \
+  } while (0)
+  if (d->bn == 64) STP3_LAUNCH_CONV(64);
+  else if (d->bn == 128) STP3_LAUNCH_CONV(128);
+  else STP3_LAUNCH_CONV(256);
+#undef STP3_LAUNCH_CONV
+  STP3_CUDA_OK(cudaGetLastError());
+  return STP3_OK;
+}

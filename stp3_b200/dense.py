@@ -1,0 +1,159 @@
+"""Host side of the dense (tensor-core) path: activation container, weight folding/packing, conv launcher.
+
+Activations live on the device channels-last as two bf16 planes (hi, lo) with channels padded to a multiple of 64;
+weights are folded (eval-mode BatchNorm -> scale/shift, reference: nn.BatchNorm eps 1e-5) and packed once per
+checkpoint load into the tap-major / K-major layout stp3_conv_fwd expects (include/stp3_b200.h).
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+KB = 64  # channels per K block
+
+
+def pad_to(c: int, m: int = KB) -> int:
+    return (c + m - 1) // m * m
+
+
+def out_tile(c: int) -> int:
+    """Padded output-channel tile of the conv kernel (UMMA N): 64, 128 or 256."""
+    for bn in (64, 128, 256):
+        if c <= bn:
+            return bn
+    raise ValueError(f"{c} output channels: split the convolution (max 256 per launch)")
+
+
+@dataclass
+class HL:
+    """(B, T, H, W, Cp) fp32 tensor carried as bf16 hi/lo planes; `c` = number of real channels."""
+    hi: torch.Tensor
+    lo: torch.Tensor
+    c: int
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @staticmethod
+    def empty(B, T, H, W, c, device, cp=None):
+        cp = cp or pad_to(c)
+        return HL(torch.empty((B, T, H, W, cp), dtype=torch.bfloat16, device=device),
+                  torch.empty((B, T, H, W, cp), dtype=torch.bfloat16, device=device), c)
+
+    @staticmethod
+    def zeros(B, T, H, W, c, device, cp=None):
+        cp = cp or pad_to(c)
+        return HL(torch.zeros((B, T, H, W, cp), dtype=torch.bfloat16, device=device),
+                  torch.zeros((B, T, H, W, cp), dtype=torch.bfloat16, device=device), c)
+
+
+def split_hilo(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def fold_bn(weight: torch.Tensor, bn: Optional[torch.nn.modules.batchnorm._BatchNorm], conv_bias=None):
+    """conv (no bias) -> eval BatchNorm  ==  conv with w*s and bias (beta - mean*s), s = gamma/sqrt(var+eps)."""
+    cout = weight.shape[0]
+    w = weight.detach().float()
+    b = conv_bias.detach().float() if conv_bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * s.view(-1, *([1] * (w.dim() - 1)))
+        b = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return w, b
+
+
+@dataclass
+class PackedConv:
+    w: torch.Tensor            # [ntaps][cin_p/64][2][bn][64] bf16
+    bias: torch.Tensor         # [bn] fp32
+    taps: List[Tuple[int, int, int]]
+    cin_p: int
+    bn: int
+    cout: int
+    stride: int
+
+
+def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dilation: int = 1,
+              padding: Optional[int] = None, causal_time: bool = True, cin_p: Optional[int] = None,
+              bn: Optional[int] = None, prune_extent: Optional[Tuple[int, int]] = None) -> PackedConv:
+    """weight: (Cout, Cin, kh, kw) or (Cout, Cin, kt, kh, kw), already BN-folded; bias (Cout).
+    Taps are (dt, dy, dx) input offsets: dy = ky*dilation - padding (padding defaults to 'same'); for 3-D kernels
+    dt = kt_index - (kt - 1) (causal: the reference pads time on the left only, temporal.py:256-262)."""
+    if weight.dim() == 4:
+        weight = weight.unsqueeze(2)
+    cout, cin, kt, kh, kw = weight.shape
+    pad_h = padding if padding is not None else (kh - 1) * dilation // 2
+    pad_w = padding if padding is not None else (kw - 1) * dilation // 2
+    cin_p = cin_p or pad_to(cin)
+    bn = bn or out_tile(cout)
+    dev = weight.device
+    taps, mats = [], []
+    for it in range(kt):
+        for iy in range(kh):
+            for ix in range(kw):
+                dy, dx = iy * dilation - pad_h, ix * dilation - pad_w
+                if prune_extent is not None and stride == 1:
+                    # a tap whose shift exceeds the image reads only zero padding for every output pixel
+                    H, W = prune_extent
+                    if abs(dy) >= H or abs(dx) >= W:
+                        continue
+                taps.append((it - (kt - 1) if causal_time else it, dy, dx))
+                m = torch.zeros((bn, cin_p), dtype=torch.float32, device=dev)
+                m[:cout, :cin] = weight[:, :, it, iy, ix]
+                mats.append(m)
+    w = torch.stack(mats)                                            # (ntaps, bn, cin_p)
+    hi, lo = split_hilo(w)
+    nt = len(taps)
+    kbs = cin_p // KB
+    packed = torch.stack([hi.view(nt, bn, kbs, KB), lo.view(nt, bn, kbs, KB)], dim=0)   # (2, nt, bn, kbs, 64)
+    packed = packed.permute(1, 3, 0, 2, 4).contiguous()              # (nt, kbs, 2, bn, 64)
+    b = torch.zeros(bn, dtype=torch.float32, device=dev)
+    b[:cout] = bias
+    return PackedConv(packed, b, taps, cin_p, bn, cout, stride)
+
+
+def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, out_coff: int = 0, relu: bool = False,
+         img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
+         res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
+         out_hw: Optional[Tuple[int, int]] = None) -> Optional[HL]:
+    """y = act(conv(x[..., cin_off:cin_off+cin]) + bias + img_bias [+ residual]) written into out[..., out_coff:...]."""
+    B, T, H, W, cs = x.hi.shape
+    Ho, Wo = out_hw if out_hw is not None else ((H + pc.stride - 1) // pc.stride, (W + pc.stride - 1) // pc.stride)
+    d = _lib.ConvDesc()
+    d.B, d.T, d.H, d.W = B, T, H, W
+    d.in_cstride, d.cin_off, d.cin = cs, cin_off, pc.cin_p
+    d.Ho, d.Wo, d.stride = Ho, Wo, pc.stride
+    d.ntaps = len(pc.taps)
+    for i, (dt, dy, dx) in enumerate(pc.taps):
+        d.taps[i][0], d.taps[i][1], d.taps[i][2] = dt, dy, dx
+    d.bn = pc.bn
+    if out is None and out_f32 is None:
+        out = HL.empty(B, T, Ho, Wo, pc.cout, x.hi.device, cp=pc.bn)
+    if out is not None:
+        assert out.hi.shape[:4] == (B, T, Ho, Wo), (out.hi.shape, (B, T, Ho, Wo))
+        d.out_cstride, d.out_coff = out.hi.shape[-1], out_coff
+    d.relu = int(relu)
+    if residual is not None:
+        d.res_mode = 2 if res_after_act else 1
+        d.res_cstride, d.res_coff = residual.hi.shape[-1], res_coff
+        assert residual.hi.shape[:4] == (B, T, Ho, Wo)
+    d.n_valid, d.sigmoid = n_valid, int(sigmoid)
+    if img_bias is not None:
+        assert img_bias.shape == (B * T, pc.bn) and img_bias.dtype == torch.float32 and img_bias.is_contiguous()
+    dev = x.hi.device
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(dev):
+        code = _lib.lib().stp3_conv_fwd(
+            ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), ptr(img_bias),
+            ptr(residual.hi if residual is not None else None), ptr(residual.lo if residual is not None else None),
+            ptr(out.hi if out is not None else None), ptr(out.lo if out is not None else None), ptr(out_f32),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(code, "stp3_conv_fwd")
+    return out

@@ -1,0 +1,119 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (through the C ABI) against a float64 PyTorch convolution of
+the same op (this is a floating-point kernel, so a torch reference is the oracle; tolerance stated per test)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from stp3_b200 import dense
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 3e-5   # of max|ref|: bf16x3 products (2^-16) with fp32 accumulation
+
+
+def to_hl(x, cp=None):
+    """x (B,T,C,H,W) fp32 on cpu -> HL on device (test helper; the product path has its own CUDA layout kernels)."""
+    B, T, C, H, W = x.shape
+    cp = cp or dense.pad_to(C)
+    xp = torch.zeros(B, T, H, W, cp)
+    xp[..., :C] = x.permute(0, 1, 3, 4, 2)
+    hi, lo = dense.split_hilo(xp.to(DEV))
+    return dense.HL(hi.contiguous(), lo.contiguous(), C)
+
+
+def from_hl(h, c0=0, c=None):
+    c = c if c is not None else h.c
+    y = h.hi.float() + h.lo.float()
+    return y[..., c0:c0 + c].permute(0, 1, 4, 2, 3).cpu()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+def ref_conv2d(x, w, b, stride=1, dilation=1, padding=None):
+    B, T, C, H, W = x.shape
+    k = w.shape[-1]
+    padding = padding if padding is not None else (k - 1) * dilation // 2
+    y = F.conv2d(x.reshape(B * T, C, H, W).double(), w.double(), b.double(), stride=stride, padding=padding,
+                 dilation=dilation)
+    return y.view(B, T, *y.shape[1:])
+
+
+def check(y, ref, tol=TOL):
+    err = (y.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * scale, (err, scale, err / scale)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,hw", [
+    (64, 64, 1, 1, 1, (20, 24)),      # 1x1, partial tiles
+    (35, 35, 3, 1, 1, (33, 17)),      # padded channels
+    (64, 128, 3, 1, 12, (40, 40)),    # ASPP dilation
+    (64, 128, 3, 2, 1, (36, 36)),     # stride 2
+    (64, 64, 7, 2, 1, (50, 50)),      # decoder.first_conv
+    (128, 256, 3, 1, 1, (25, 25)),    # two K blocks, BN=256
+    (64, 128, 1, 2, 1, (20, 20)),     # resnet downsample 1x1 stride 2
+    (256, 128, 1, 1, 1, (16, 16)),    # four K blocks
+])
+def test_conv2d_matches_fp64(cin, cout, k, stride, dil, hw):
+    H, W = hw
+    x = rnd(2, 2, cin, H, W, seed=1)
+    w = rnd(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5)
+    b = rnd(cout, seed=3)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV), stride=stride, dilation=dil)
+    y = dense.conv(to_hl(x), pc)
+    torch.cuda.synchronize()
+    ref = ref_conv2d(x, w, b, stride=stride, dilation=dil)
+    out = from_hl(y, 0, cout)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    check(out, ref)
+    if pc.bn > cout:   # padded output channels are exactly zero (zero weights, zero bias)
+        assert float((y.hi[..., cout:].float().abs() + y.lo[..., cout:].float().abs()).max()) == 0.0
+
+
+def test_causal_conv3d():
+    """CausalConv3d (2,3,3): time padded on the left only (temporal.py:252-273)."""
+    B, T, C, H, W = 2, 3, 35, 24, 20
+    x = rnd(B, T, C, H, W, seed=4)
+    w = rnd(35, C, 2, 3, 3, seed=5, scale=0.05)
+    b = rnd(35, seed=6)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    y = dense.conv(to_hl(x), pc, relu=True)
+    xp = F.pad(x.permute(0, 2, 1, 3, 4).double(), (1, 1, 1, 1, 1, 0))
+    ref = F.relu(F.conv3d(xp, w.double(), b.double())).permute(0, 2, 1, 3, 4)
+    check(from_hl(y, 0, 35), ref)
+
+
+def test_epilogue_fusions():
+    B, T, C, H, W = 1, 3, 64, 19, 21
+    x = rnd(B, T, C, H, W, seed=7)
+    w = rnd(64, C, 3, 3, seed=8, scale=0.05)
+    b = rnd(64, seed=9)
+    res = rnd(B, T, 64, H, W, seed=10)
+    ib = rnd(B * T, 64, seed=11)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    base = ref_conv2d(x, w, b) + ib.view(B, T, 64, 1, 1).double()
+    # residual before the activation (ResNet BasicBlock), written at a channel offset of a wider tensor
+    out = dense.HL.zeros(B, T, H, W, 192, DEV)
+    dense.conv(to_hl(x), pc, out=out, out_coff=64, relu=True, img_bias=ib.to(DEV), residual=to_hl(res))
+    check(from_hl(out, 64, 64), F.relu(base + res.double()))
+    assert float(out.hi[..., :64].float().abs().max()) == 0.0 and float(out.hi[..., 128:].float().abs().max()) == 0.0
+    # residual after the activation (TemporalBlock skip)
+    y = dense.conv(to_hl(x), pc, relu=True, img_bias=ib.to(DEV), residual=to_hl(res), res_after_act=True)
+    check(from_hl(y), F.relu(base) + res.double())
+    # fp32 NCHW output of the first 5 channels with sigmoid
+    o32 = torch.empty(B * T, 5, H, W, device=DEV)
+    dense.conv(to_hl(x), pc, img_bias=ib.to(DEV), out_f32=o32, n_valid=5, sigmoid=True)
+    check(o32.view(B, T, 5, H, W).cpu(), torch.sigmoid(base[:, :, :5]), tol=1e-5)
+
+
+def test_channel_window_input():
+    """cin_off: read a 64-channel window of a wider (concat) tensor."""
+    x = rnd(1, 1, 128, 16, 16, seed=12)
+    w = rnd(64, 64, 1, 1, seed=13, scale=0.1)
+    b = torch.zeros(64)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    y = dense.conv(to_hl(x), pc, cin_off=64)
+    check(from_hl(y), ref_conv2d(x[:, :, 64:], w, b))
