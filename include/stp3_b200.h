@@ -58,7 +58,9 @@ const char* stp3_last_error(void);
  *                 ego warp, -1 where the reference's mask (stp3.py:239-246) drops it.  Bit-exact with the CPU
  *                 reference; used by the parity tests.
  *   out           out_layout==0: (B,S,C,nx,ny) fp32  [what projection_to_birds_eye_view returns]
- *                 out_layout==1: (B,S,nx,ny,C) fp32  [channels-last, consumed by the temporal block kernels]
+ *                 out_layout==1: (B,S,nx,ny,C) fp32  [channels-last]
+ *                 out_layout==2: two bf16 planes [2][B,S,nx,ny,C] (hi then lo; C % 8 == 0): the activation format
+ *                                of the tensor-core path, consumed directly by stp3_conv_fwd
  *   pool_sum      optional (B,S,C) fp32: sum over the nx*ny cells of out[b,t,c] (feeds the pyramid-pooling branch
  *                 of TemporalBlock, temporal.py:408-423); must be zero-initialised by the caller.
  *   workspace     >= stp3_lift_splat_workspace_bytes(...) bytes, 256-byte aligned.  It holds the channels-last
@@ -104,7 +106,9 @@ int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_l
  * outside the tensor read as zero (this is the reference's zero / causal padding).
  */
 typedef struct stp3_conv_desc {
-  int B, T, H, W;        /* input: B samples x T frames of H x W pixels */
+  int B, T, H, W;        /* B samples x T frames are processed; the input tensor is (B, T_total, H, W, in_cstride) */
+  int T_total, t0;       /* frames [t0, t0+T) of each sample are processed (T_total = 0 means T_total = T, t0 = 0);
+                            outputs / residual / img_bias are indexed by the B*T processed images */
   int in_cstride;        /* channels of the input tensor */
   int cin_off, cin;      /* channel window this convolution reads (multiples of 64) */
   int Ho, Wo;            /* output spatial size */
@@ -113,6 +117,8 @@ typedef struct stp3_conv_desc {
   signed char taps[49][3];
   int bn;                /* padded output channels: 64, 128 or 256 */
   int out_cstride, out_coff;
+  int n_store;           /* output channels actually stored to y_hi/y_lo (multiple of 8, 0 = bn): lets several
+                            convolutions write adjacent windows of one concat tensor */
   int relu;              /* apply ReLU */
   int res_mode;          /* 0 none, 1 residual added before the activation, 2 after it */
   int res_cstride, res_coff;
@@ -123,6 +129,35 @@ typedef struct stp3_conv_desc {
 int stp3_conv_fwd(const stp3_conv_desc* desc, const void* x_hi, const void* x_lo, const void* w, const float* bias,
                   const float* img_bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
                   float* y_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Memory-bound helpers of the dense path (all tensors channels-last bf16 hi/lo planes unless noted).
+ */
+/* fp32 (n_img,C,H,W) [channels_last=0, the reference's NCHW] or (n_img,H,W,C) [1] -> hi/lo (n_img,H,W,cp), padding 0.
+ * Used where a foreign fp32 tensor enters a drop-in module (e.g. TemporalModel.forward, temporal_model.py:50). */
+int stp3_f32_to_hilo(const float* x, int channels_last, int n_img, int C, int H, int W, int cp, void* hi, void* lo,
+                     void* stream);
+/* hi/lo (n_img,H,W,cstride) channels [c_off, c_off+C) -> fp32 (n_img,C,H,W): module outputs in the reference layout */
+int stp3_hilo_to_f32(const void* hi, const void* lo, int n_img, int H, int W, int cstride, int c_off, int C, float* out,
+                     void* stream);
+/* sums[img][c] = sum over the H*W pixels (fp32, (n_img, cstride)); cstride <= 1024 */
+int stp3_spatial_sum(const void* hi, const void* lo, int n_img, int HW, int cstride, float* sums, void* stream);
+/* Spatially constant branches folded to a per-image bias of the consuming 1x1 convolution:
+ *   m = sums * inv_hw (temporal != 0: averaged with the previous frame of the same sample when it exists --
+ *       AvgPool3d((2,H,W), padding (1,0,0), count_include_pad=False), temporal.py:397-415)
+ *   v = relu(W1 m + b1)  (R);   out[img][co] (+)= sum_r W2[co][r] v[r]
+ * Replaces PyramidSpatioTemporalPooling (temporal.py:375-423) and ASPPPooling (convolutions.py:227-239). */
+int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int T, int C, float inv_hw, int temporal,
+                   const float* W1, const float* b1, int R, const float* W2, int CO, float* out, int co_stride,
+                   int accumulate, void* stream);
+/* y[n][co] (+)= sum_ci W[co][ci] x[n][ci]: the 6 broadcast ego-motion channels of stp3.py:145-152 as a bias */
+int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, float* y, int co_stride, int accumulate,
+                      void* stream);
+/* UpsamplingAdd tail (convolutions.py:204-215): y = bilinear_x2(x) + skip[..., s_coff:s_coff+C]; x is (n_img,h,w,.),
+ * skip and y are (n_img,2h,2w,.) */
+int stp3_upsample2x_add(const void* x_hi, const void* x_lo, int n_img, int h, int w, int x_cstride, const void* s_hi,
+                        const void* s_lo, int s_cstride, int s_coff, void* y_hi, void* y_lo, int y_cstride, int C,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,9 @@ _SZ = ctypes.c_size_t
 _FP = ctypes.POINTER(ctypes.c_float)
 class ConvDesc(ctypes.Structure):
     """Mirror of stp3_conv_desc (include/stp3_b200.h)."""
-    _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("in_cstride", _I), ("cin_off", _I), ("cin", _I),
+    _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("T_total", _I), ("t0", _I), ("in_cstride", _I), ("cin_off", _I), ("cin", _I),
                 ("Ho", _I), ("Wo", _I), ("stride", _I), ("ntaps", _I), ("taps", (ctypes.c_byte * 3) * 49),
-                ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("relu", _I), ("res_mode", _I),
+                ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("n_store", _I), ("relu", _I), ("res_mode", _I),
                 ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I)]
 
 
@@ -33,6 +33,12 @@ SIGNATURES = {
     "stp3_last_error": (ctypes.c_char_p, []),
     "stp3_lift_splat_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "stp3_lift_splat_workspace_init": (_I, [_V, _SZ, _V]),
+    "stp3_f32_to_hilo": (_I, [_V, _I, _I, _I, _I, _I, _I, _V, _V, _V]),
+    "stp3_hilo_to_f32": (_I, [_V, _V, _I, _I, _I, _I, _I, _I, _V, _V]),
+    "stp3_spatial_sum": (_I, [_V, _V, _I, _I, _I, _V, _V]),
+    "stp3_pool_bias": (_I, [_V, _I, _I, _I, _I, _F, _I, _V, _V, _I, _V, _I, _V, _I, _I, _V]),
+    "stp3_small_linear": (_I, [_V, _V, _I, _I, _I, _V, _I, _I, _V]),
+    "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _V]),
     "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
                                  _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,

@@ -30,7 +30,7 @@ constexpr int kBK = 64;                         // channels per K step (one 128-
 constexpr int kMaxTaps = 49;
 
 struct ConvParams {
-  int n_img, T, Ho, Wo;
+  int n_img, T, t0, Ho, Wo;
   int tiles_x, tiles_y;
   int stride;
   int kblocks;              // Cin / 64 of this convolution
@@ -46,7 +46,7 @@ struct ConvParams {
   int res_cstride, res_coff;
   __nv_bfloat16* out_hi;    // channels-last (n_img, Ho, Wo, out_cstride), may be null when out_f32 is used
   __nv_bfloat16* out_lo;
-  int out_cstride, out_coff;
+  int out_cstride, out_coff, n_store;
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
   int n_valid;
   int sigmoid;              // apply to out_f32 (instance_center head)
@@ -80,7 +80,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   const int tx = tile % p.tiles_x; tile /= p.tiles_x;
   const int ty = tile % p.tiles_y; tile /= p.tiles_y;
   const int img = tile;
-  const int bidx = img / p.T, tidx = img % p.T;
+  const int bidx = img / p.T, tidx = p.t0 + img % p.T;
   const int ox0 = tx * kTileW, oy0 = ty * kTileH;
   const int k_iters = p.ntaps * p.kblocks;
 
@@ -193,6 +193,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + j * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            if (j * 32 + g * 8 >= p.n_store) break;
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -254,12 +255,16 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   STP3_CHECK_ARG(d && x_hi && x_lo && w && bias, "stp3_conv_fwd: null pointer argument");
   STP3_CHECK_ARG((y_hi && y_lo) || y_f32, "stp3_conv_fwd: no output tensor");
   STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "non-positive dimension");
+  const int T_total = d->T_total > 0 ? d->T_total : d->T;
+  STP3_CHECK_ARG(d->t0 >= 0 && d->t0 + d->T <= T_total, "frame window [t0, t0+T) outside the input tensor");
+  const int n_store = d->n_store > 0 ? d->n_store : d->bn;
+  STP3_CHECK_ARG(n_store % 8 == 0 && n_store <= d->bn, "n_store must be a multiple of 8 and <= bn");
   STP3_CHECK_ARG(d->in_cstride % 64 == 0 && d->cin % 64 == 0 && d->cin_off % 64 == 0 && d->cin > 0 &&
                  d->cin_off + d->cin <= d->in_cstride, "input channels must be padded to multiples of 64");
   STP3_CHECK_ARG(d->bn == 64 || d->bn == 128 || d->bn == 256, "bn (padded output channels) must be 64, 128 or 256");
   STP3_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   STP3_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "ntaps out of range");
-  if (y_hi) STP3_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->bn <= d->out_cstride,
+  if (y_hi) STP3_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + n_store <= d->out_cstride,
                            "output channel window does not fit the output tensor");
   if (d->res_mode) STP3_CHECK_ARG(res_hi && res_lo && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 &&
                                   d->res_coff + d->bn <= d->res_cstride, "bad residual tensor");
@@ -269,11 +274,11 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)d->in_cstride, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->T,
+    const cuuint64_t dims[5] = {(cuuint64_t)d->in_cstride, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)T_total,
                                 (cuuint64_t)d->B};
     const cuuint64_t strides[4] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
                                    (cuuint64_t)d->H * d->W * d->in_cstride * 2,
-                                   (cuuint64_t)d->T * d->H * d->W * d->in_cstride * 2};
+                                   (cuuint64_t)T_total * d->H * d->W * d->in_cstride * 2};
     const cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)((kTileW - 1) * d->stride + 1),
                                (cuuint32_t)((kTileH - 1) * d->stride + 1), 1, 1};
     const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
@@ -299,7 +304,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   }
 
   ConvParams p;
-  p.n_img = d->B * d->T; p.T = d->T; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, kTileH);
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
@@ -307,7 +312,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
   p.res_cstride = d->res_cstride; p.res_coff = d->res_coff;
   p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
-  p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+  p.out_cstride = d->out_cstride; p.out_coff = d->out_coff; p.n_store = n_store;
   p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
 
   const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;

@@ -17,6 +17,8 @@
 //         and never needs a memset.
 //
 // Reference semantics: /root/reference/stp3/models/stp3.py:186-301, stp3/utils/geometry.py:299-318.
+#include <cuda_bf16.h>
+
 #include <cmath>
 #include <cstdint>
 
@@ -382,7 +384,21 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(__fmul_rn(acc[i], discount), v[t][i]);
       if (valid) {
-        if (out_nhwc) {
+        if (out_nhwc == 2) {               // bf16 hi/lo planes for the tensor-core path (VEC only)
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(out) + (bt * nvox + pcell) * C + c0;
+          __nv_bfloat16* lp = hp + (size_t)gridDim.y * S * nvox * C;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * e]), h1 = __float2bfloat16_rn(acc[2 * e + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[2 * e] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(acc[2 * e + 1] - __bfloat162float(h1));
+            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        } else if (out_nhwc) {
           float* dst = out + (bt * nvox + pcell) * C + c0;
           if (VEC) {
             __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
@@ -480,7 +496,8 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   STP3_CHECK_ARG(nz == 1, "nz=%d: the reference (stp3.py:298) and this kernel support a single height bin", nz);
   STP3_CHECK_ARG((long long)nx * ny * nz < (1ll << 31), "BEV grid too large for int32 ranks");
   STP3_CHECK_ARG(feat_layout == 0 || feat_layout == 1, "feat_layout must be 0 (NCHW) or 1 (NHWC)");
-  STP3_CHECK_ARG(out_layout == 0 || out_layout == 1, "out_layout must be 0 (C,X,Y) or 1 (X,Y,C)");
+  STP3_CHECK_ARG(out_layout >= 0 && out_layout <= 2, "out_layout must be 0 (C,X,Y), 1 (X,Y,C) or 2 (bf16 hi/lo X,Y,C)");
+  STP3_CHECK_ARG(out_layout != 2 || C % 8 == 0, "out_layout 2 needs C %% 8 == 0");
   STP3_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   const size_t need = stp3_lift_splat_workspace_bytes(B, S, C, nx, ny);
   if (workspace_bytes < need) return set_error(STP3_ENOSPC, "workspace too small: %zu < %zu", workspace_bytes, need);

@@ -82,7 +82,8 @@ class PackedConv:
 
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dilation: int = 1,
               padding: Optional[int] = None, causal_time: bool = True, cin_p: Optional[int] = None,
-              bn: Optional[int] = None, prune_extent: Optional[Tuple[int, int]] = None) -> PackedConv:
+              bn: Optional[int] = None, prune_extent: Optional[Tuple[int, int]] = None,
+              in_layout: Optional[Sequence[Tuple[int, int, int]]] = None) -> PackedConv:
     """weight: (Cout, Cin, kh, kw) or (Cout, Cin, kt, kh, kw), already BN-folded; bias (Cout).
     Taps are (dt, dy, dx) input offsets: dy = ky*dilation - padding (padding defaults to 'same'); for 3-D kernels
     dt = kt_index - (kt - 1) (causal: the reference pads time on the left only, temporal.py:256-262)."""
@@ -91,7 +92,10 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     cout, cin, kt, kh, kw = weight.shape
     pad_h = padding if padding is not None else (kh - 1) * dilation // 2
     pad_w = padding if padding is not None else (kw - 1) * dilation // 2
-    cin_p = cin_p or pad_to(cin)
+    # in_layout: [(first logical input channel, count, physical channel offset)] -- where each group of the
+    # convolution's input channels lives inside the (padded / concatenated) physical input window
+    in_layout = list(in_layout) if in_layout is not None else [(0, cin, 0)]
+    cin_p = cin_p or pad_to(max(off + n for _, n, off in in_layout))
     bn = bn or out_tile(cout)
     dev = weight.device
     taps, mats = [], []
@@ -106,7 +110,8 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
                         continue
                 taps.append((it - (kt - 1) if causal_time else it, dy, dx))
                 m = torch.zeros((bn, cin_p), dtype=torch.float32, device=dev)
-                m[:cout, :cin] = weight[:, :, it, iy, ix]
+                for src, n, off in in_layout:
+                    m[:cout, off:off + n] = weight[:, src:src + n, it, iy, ix]
                 mats.append(m)
     w = torch.stack(mats)                                            # (ntaps, bn, cin_p)
     hi, lo = split_hilo(w)
@@ -122,12 +127,15 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
 def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, out_coff: int = 0, relu: bool = False,
          img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
-         out_hw: Optional[Tuple[int, int]] = None) -> Optional[HL]:
+         out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None
+         ) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias + img_bias [+ residual]) written into out[..., out_coff:...]."""
-    B, T, H, W, cs = x.hi.shape
+    B, T_total, H, W, cs = x.hi.shape
+    t0, T = frames if frames is not None else (0, T_total)      # process frames [t0, t0+T) of every sample
     Ho, Wo = out_hw if out_hw is not None else ((H + pc.stride - 1) // pc.stride, (W + pc.stride - 1) // pc.stride)
     d = _lib.ConvDesc()
     d.B, d.T, d.H, d.W = B, T, H, W
+    d.T_total, d.t0 = T_total, t0
     d.in_cstride, d.cin_off, d.cin = cs, cin_off, pc.cin_p
     d.Ho, d.Wo, d.stride = Ho, Wo, pc.stride
     d.ntaps = len(pc.taps)
@@ -138,7 +146,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         out = HL.empty(B, T, Ho, Wo, pc.cout, x.hi.device, cp=pc.bn)
     if out is not None:
         assert out.hi.shape[:4] == (B, T, Ho, Wo), (out.hi.shape, (B, T, Ho, Wo))
-        d.out_cstride, d.out_coff = out.hi.shape[-1], out_coff
+        d.out_cstride, d.out_coff, d.n_store = out.hi.shape[-1], out_coff, n_store
     d.relu = int(relu)
     if residual is not None:
         d.res_mode = 2 if res_after_act else 1
@@ -156,4 +164,90 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
             ptr(out.hi if out is not None else None), ptr(out.lo if out is not None else None), ptr(out_f32),
             torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(code, "stp3_conv_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ aux kernels
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def from_f32(x: torch.Tensor, channels_last: bool = False, cp: Optional[int] = None) -> HL:
+    """x (B,T,C,H,W) [or (B,T,H,W,C)] fp32 on the device -> HL (CUDA transpose + hi/lo split)."""
+    if not x.is_cuda:
+        raise RuntimeError("stp3_b200 dense ops run on CUDA tensors only (there is no CPU path)")
+    x = x.detach().float().contiguous()
+    if channels_last:
+        B, T, H, W, C = x.shape
+    else:
+        B, T, C, H, W = x.shape
+    out = HL.empty(B, T, H, W, C, x.device, cp=cp)
+    with torch.cuda.device(x.device):
+        code = _lib.lib().stp3_f32_to_hilo(x.data_ptr(), int(channels_last), B * T, C, H, W, out.hi.shape[-1],
+                                           out.hi.data_ptr(), out.lo.data_ptr(), _stream(x.device))
+    _lib.check(code, "stp3_f32_to_hilo")
+    return out
+
+
+def to_f32(x: HL, c_off: int = 0, c: Optional[int] = None) -> torch.Tensor:
+    """HL -> (B,T,C,H,W) fp32 (the reference's layout)."""
+    B, T, H, W, cs = x.hi.shape
+    c = c if c is not None else x.c
+    out = torch.empty((B, T, c, H, W), dtype=torch.float32, device=x.hi.device)
+    with torch.cuda.device(x.hi.device):
+        code = _lib.lib().stp3_hilo_to_f32(x.hi.data_ptr(), x.lo.data_ptr(), B * T, H, W, cs, c_off, c, out.data_ptr(),
+                                           _stream(x.hi.device))
+    _lib.check(code, "stp3_hilo_to_f32")
+    return out
+
+
+def spatial_sum(x: HL) -> torch.Tensor:
+    """(B*T, cstride) fp32 sums over the H*W pixels of every image."""
+    B, T, H, W, cs = x.hi.shape
+    out = torch.empty((B * T, cs), dtype=torch.float32, device=x.hi.device)
+    with torch.cuda.device(x.hi.device):
+        code = _lib.lib().stp3_spatial_sum(x.hi.data_ptr(), x.lo.data_ptr(), B * T, H * W, cs, out.data_ptr(),
+                                           _stream(x.hi.device))
+    _lib.check(code, "stp3_spatial_sum")
+    return out
+
+
+def pool_bias(sums: torch.Tensor, T: int, C: int, hw: int, temporal: bool, W1, b1, W2, out: torch.Tensor,
+              accumulate: bool):
+    """out[img, :CO] (+)= W2 relu(W1 mean + b1): a spatially constant branch as a per-image bias (see header)."""
+    n_img = sums.shape[0]
+    R, CO = W1.shape[0], W2.shape[0]
+    assert W1.shape == (R, C) and W2.shape == (CO, R) and out.shape[0] == n_img
+    for t in (sums, W1, b1, W2, out):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    with torch.cuda.device(sums.device):
+        code = _lib.lib().stp3_pool_bias(sums.data_ptr(), sums.shape[1], n_img, T, C, 1.0 / hw, int(temporal),
+                                         W1.data_ptr(), b1.data_ptr(), R, W2.data_ptr(), CO, out.data_ptr(),
+                                         out.shape[1], int(accumulate), _stream(sums.device))
+    _lib.check(code, "stp3_pool_bias")
+
+
+def small_linear(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor, accumulate: bool):
+    """out[n, :co] (+)= W x[n]."""
+    n, ci = x.shape
+    co = W.shape[0]
+    assert W.shape == (co, ci) and out.shape[0] == n
+    for t in (x, W, out):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    with torch.cuda.device(x.device):
+        code = _lib.lib().stp3_small_linear(x.data_ptr(), W.data_ptr(), n, ci, co, out.data_ptr(), out.shape[1],
+                                            int(accumulate), _stream(x.device))
+    _lib.check(code, "stp3_small_linear")
+
+
+def upsample2x_add(x: HL, skip: HL, c: int, skip_coff: int = 0) -> HL:
+    """bilinear x2 (align_corners=False) of x plus skip[..., skip_coff:skip_coff+c]."""
+    B, T, h, w, xs = x.hi.shape
+    assert skip.hi.shape[:4] == (B, T, 2 * h, 2 * w)
+    out = HL.empty(B, T, 2 * h, 2 * w, c, x.hi.device, cp=c)
+    with torch.cuda.device(x.hi.device):
+        code = _lib.lib().stp3_upsample2x_add(x.hi.data_ptr(), x.lo.data_ptr(), B * T, h, w, xs, skip.hi.data_ptr(),
+                                              skip.lo.data_ptr(), skip.hi.shape[-1], skip_coff, out.hi.data_ptr(),
+                                              out.lo.data_ptr(), c, c, _stream(x.hi.device))
+    _lib.check(code, "stp3_upsample2x_add")
     return out

@@ -1,0 +1,191 @@
+"""3-D spatio-temporal block with the reference's constructor signatures and parameter names
+(stp3/layers/temporal.py:252-273, 315-325, 375-489); forward() runs on the tcgen05 implicit-GEMM kernels.
+
+TemporalBlock data flow on the device (channels-last hi/lo planes, o = half rounded up to 8):
+    x --1x1x1 (paths 0,1 fused, N=128)--> mid[0:half | 64:64+half]
+    mid[0:64]  --causal (2,3,3)--> agg[0:o]         mid[64:128] --(1,3,3)--> agg[o:2o]
+    x --1x1x1 (path 2)--> agg[2o:3o]
+    pyramid pooling (spatially constant, temporal.py:408-423)  -> per-image bias of the aggregation conv
+    out = relu(BN(1x1x1(agg))) + (projection(x) | x)
+Spatially constant input channels (the broadcast ego-motion of stp3.py:145-152) are never materialised: they enter
+every 1x1x1 convolution that reads x as a per-image bias.
+"""
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import dense
+from ._packing import PackedModule
+
+
+def conv_1x1x1_norm_activated(in_channels, out_channels):
+    """1x1x1 Conv3d (no bias) + BatchNorm3d + ReLU, named conv / norm / activation as in the reference."""
+    return nn.Sequential(OrderedDict(conv=nn.Conv3d(in_channels, out_channels, kernel_size=1, bias=False),
+                                     norm=nn.BatchNorm3d(out_channels), activation=nn.ReLU(inplace=True)))
+
+
+class CausalConv3d(nn.Module):
+    """Parameter container of the causal 3-D convolution (time padded on the left only)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(2, 3, 3), dilation=(1, 1, 1), bias=False):
+        super().__init__()
+        assert len(kernel_size) == 3, 'kernel_size must be a 3-tuple.'
+        assert tuple(dilation) == (1, 1, 1), "the reference never dilates its causal convolutions"
+        kt, kh, kw = kernel_size
+        self.pad = nn.ConstantPad3d(padding=((kw - 1) // 2, (kw - 1) // 2, (kh - 1) // 2, (kh - 1) // 2, kt - 1, 0), value=0)
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, dilation=dilation, stride=1, padding=0, bias=bias)
+        self.norm = nn.BatchNorm3d(out_channels)
+        self.activation = nn.ReLU(inplace=True)
+
+
+class PyramidSpatioTemporalPooling(nn.Module):
+    """Parameter container; pool_sizes must be [(2, h, w)] with (h, w) the full map (the reference's only use),
+    which makes the branch spatially constant."""
+
+    def __init__(self, in_channels, reduction_channels, pool_sizes):
+        super().__init__()
+        feats = []
+        for pool_size in pool_sizes:
+            assert pool_size[0] == 2, "Time kernel should be 2 (as in the reference)"
+            feats.append(nn.Sequential(OrderedDict(
+                avgpool=nn.AvgPool3d(kernel_size=pool_size, stride=(1, *pool_size[1:]), padding=(pool_size[0] - 1, 0, 0),
+                                     count_include_pad=False),
+                conv_bn_relu=conv_1x1x1_norm_activated(in_channels, reduction_channels))))
+        self.features = nn.ModuleList(feats)
+        self.pool_sizes = [tuple(p) for p in pool_sizes]
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+class TemporalBlock(PackedModule):
+    def __init__(self, in_channels, out_channels=None, use_pyramid_pooling=False, pool_sizes=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.half_channels = in_channels // 2
+        self.out_channels = out_channels or self.in_channels
+        self.kernels = [(2, 3, 3), (1, 3, 3)]
+        self.use_pyramid_pooling = use_pyramid_pooling
+
+        paths = [nn.Sequential(conv_1x1x1_norm_activated(self.in_channels, self.half_channels),
+                               CausalConv3d(self.half_channels, self.half_channels, kernel_size=k))
+                 for k in self.kernels]
+        paths.append(conv_1x1x1_norm_activated(self.in_channels, self.half_channels))
+        self.convolution_paths = nn.ModuleList(paths)
+        agg_in_channels = len(self.convolution_paths) * self.half_channels
+
+        if self.use_pyramid_pooling:
+            assert pool_sizes is not None, "setting must contain the list of kernel_size, but is None."
+            assert len(pool_sizes) == 1, "one full-map pool size, as in the reference (temporal_model.py:24)"
+            reduction_channels = self.in_channels // 3
+            self.pyramid_pooling = PyramidSpatioTemporalPooling(self.in_channels, reduction_channels, pool_sizes)
+            agg_in_channels += len(pool_sizes) * reduction_channels
+
+        self.aggregation = nn.Sequential(conv_1x1x1_norm_activated(agg_in_channels, self.out_channels),)
+
+        if self.out_channels != self.in_channels:
+            self.projection = nn.Sequential(
+                nn.Conv3d(self.in_channels, self.out_channels, kernel_size=1, bias=False),
+                nn.BatchNorm3d(self.out_channels),
+            )
+        else:
+            self.projection = None
+        self.n_const = 0      # trailing input channels that are spatially constant (set by STP3 for the ego-motion)
+
+    # ------------------------------------------------------------------------------------------------
+    def _pack(self):
+        cin, half, cout, nc = self.in_channels, self.half_channels, self.out_channels, self.n_const
+        cs = cin - nc                                  # spatial input channels
+        o = _round8(half)
+        assert half <= 64 and 3 * o <= 128 and cout <= 256, "channel counts beyond the reference's configurations"
+        P = {"o": o, "cs": cs}
+        flat = lambda w: w.reshape(w.shape[0], w.shape[1])
+        p0, p1, p2 = self.convolution_paths
+        # fused entry convolutions of paths 0 and 1 (N = 128: path 0 at rows 0.., path 1 at rows 64..)
+        w0, b0 = dense.fold_bn(p0[0].conv.weight, p0[0].norm)
+        w1, b1 = dense.fold_bn(p1[0].conv.weight, p1[0].norm)
+        wa = torch.zeros(128, cin, device=w0.device)
+        ba = torch.zeros(128, device=w0.device)
+        wa[:half], wa[64:64 + half] = flat(w0), flat(w1)
+        ba[:half], ba[64:64 + half] = b0, b1
+        P["a1"] = dense.pack_conv(wa[:, :cs].reshape(128, cs, 1, 1).contiguous(), ba, bn=128)
+        w2, b2 = dense.fold_bn(p2.conv.weight, p2.norm)
+        P["a2"] = dense.pack_conv(flat(w2)[:, :cs].reshape(half, cs, 1, 1).contiguous(), b2, bn=64)
+        wt, bt = dense.fold_bn(p0[1].conv.weight, p0[1].norm)          # (half, half, 2, 3, 3)
+        P["b"] = dense.pack_conv(wt, bt, cin_p=64, bn=64)
+        ws, bs = dense.fold_bn(p1[1].conv.weight, p1[1].norm)          # (half, half, 1, 3, 3)
+        P["c"] = dense.pack_conv(ws, bs, cin_p=64, bn=64)
+        wg, bg = dense.fold_bn(self.aggregation[0].conv.weight, self.aggregation[0].norm)
+        wg = flat(wg)
+        P["agg"] = dense.pack_conv(wg[:, :3 * half].reshape(cout, 3 * half, 1, 1).contiguous(), bg,
+                                   in_layout=[(0, half, 0), (half, half, o), (2 * half, half, 2 * o)], cin_p=128)
+        if self.use_pyramid_pooling:
+            wp, bp = dense.fold_bn(self.pyramid_pooling.features[0].conv_bn_relu.conv.weight,
+                                   self.pyramid_pooling.features[0].conv_bn_relu.norm)
+            P["pool_w1"], P["pool_b1"] = flat(wp).contiguous(), bp.contiguous()
+            P["pool_w2"] = wg[:, 3 * half:].contiguous()
+        if self.projection is not None:
+            wj, bj = dense.fold_bn(self.projection[0].weight, self.projection[1])
+            P["proj"] = dense.pack_conv(flat(wj)[:, :cs].reshape(cout, cs, 1, 1).contiguous(), bj)
+            P["proj_c"] = flat(wj)[:, cs:].contiguous()
+        if nc:
+            P["a1_c"] = wa[:, cs:].contiguous()
+            P["a2_c"] = flat(w2)[:, cs:].contiguous()
+        return P
+
+    def forward_hl(self, x: dense.HL, const: Optional[torch.Tensor] = None,
+                   sums: Optional[torch.Tensor] = None) -> dense.HL:
+        """x: HL (B,T,H,W,.) holding the spatial input channels; const: (B*T, n_const) fp32 values of the spatially
+        constant trailing channels (requires self.n_const == const.shape[1]); sums: optional precomputed per-image
+        spatial sums of x (B*T, >= spatial channels), e.g. emitted by the lift-splat finalize kernel."""
+        self._require_eval()
+        nc = 0 if const is None else const.shape[1]
+        assert nc == self.n_const, "set TemporalBlock.n_const to the number of spatially constant input channels"
+        P = self.packed()
+        B, T, H, W, _ = x.hi.shape
+        dev = x.hi.device
+        cin, half, cout, o, cs = self.in_channels, self.half_channels, self.out_channels, P["o"], P["cs"]
+        n_img = B * T
+
+        def const_bias(wc, bn):
+            if not nc:
+                return None
+            b = torch.empty((n_img, bn), dtype=torch.float32, device=dev)
+            dense.small_linear(const, wc, b, False)
+            return b
+
+        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), 128))
+        agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=128)
+        if 3 * o < 128:
+            agg.hi[..., 3 * o:].zero_(); agg.lo[..., 3 * o:].zero_()      # padding channels of the concat tensor
+        dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
+        dense.conv(mid, P["c"], cin_off=64, out=agg, out_coff=o, n_store=o, relu=True)
+        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=o, relu=True, img_bias=const_bias(P.get("a2_c"), 64))
+        pbias = None
+        if self.use_pyramid_pooling:
+            ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
+            assert (ph, pw) == (H, W), "pyramid pooling must span the whole map (as configured by TemporalModel)"
+            if sums is None:
+                sums = dense.spatial_sum(x)
+            full = torch.empty((n_img, cin), dtype=torch.float32, device=dev)
+            full[:, :cs] = sums[:, :cs]
+            if nc:
+                full[:, cs:] = const * float(H * W)
+            pbias = torch.empty((n_img, P["agg"].bn), dtype=torch.float32, device=dev)
+            dense.pool_bias(full, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False)
+        if self.projection is not None:
+            res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"].bn))
+        else:
+            assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
+            res = x
+        return dense.conv(agg, P["agg"], relu=True, img_bias=pbias, residual=res, res_after_act=True)
+
+    def forward(self, *inputs):
+        """x (B, C, T, H, W) fp32 -> (B, Cout, T, H, W) fp32, like the reference module."""
+        (x,) = inputs
+        assert self.n_const == 0
+        y = self.forward_hl(dense.from_f32(x.permute(0, 2, 1, 3, 4)))
+        return dense.to_f32(y, 0, self.out_channels).permute(0, 2, 1, 3, 4)

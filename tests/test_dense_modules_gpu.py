@@ -1,0 +1,137 @@
+"""GPU parity of the drop-in dense modules (TemporalBlock, DeepLabHead, TemporalModel, Decoder, UpsamplingAdd and the
+memory-bound helpers) against the plain-PyTorch oracle evaluated in float64 on the CPU with the same weights, and
+against the golden outputs of the unmodified reference.  Bar: head logits / features within 1e-3 relative (north_star);
+measured ~1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import torch_dense as TD
+from oracle.make_golden_dense import GATES_ALL, GATES_PERCEIVE, dense_input
+from stp3_b200 import dense
+from stp3_b200.layers.convolutions import DeepLabHead, UpsamplingAdd
+from stp3_b200.layers.temporal import TemporalBlock
+from stp3_b200.models.decoder import Decoder
+from stp3_b200.models.temporal_model import TemporalModel
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL = 1e-3
+
+
+def close(y, ref, rel=REL):
+    ref = ref.double()
+    err = (y.double().cpu() - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1e-6)
+    assert err <= rel * scale, (err, scale, err / scale)
+    return err / scale
+
+
+def f64(m):
+    import copy
+    return copy.deepcopy(m).double()
+
+
+def test_layout_roundtrip_and_spatial_sum():
+    x = dense_input((2, 3, 70, 13, 21), 1).to(DEV)
+    h = dense.from_f32(x)
+    assert h.hi.shape == (2, 3, 13, 21, 128) and float(h.hi[..., 70:].float().abs().max()) == 0.0
+    y = dense.to_f32(h, 0, 70)
+    assert (y - x).abs().max() <= 2e-5 * x.abs().max()            # hi+lo keeps 16 mantissa bits
+    s = dense.spatial_sum(h)
+    ref = x.double().sum(dim=(-1, -2)).view(6, 70)
+    assert torch.allclose(s[:, :70].double(), ref, rtol=1e-4, atol=1e-3)
+    hcl = dense.from_f32(x.permute(0, 1, 3, 4, 2).contiguous(), channels_last=True)
+    assert torch.equal(hcl.hi, h.hi) and torch.equal(hcl.lo, h.lo)
+
+
+def test_upsampling_add():
+    with torch.no_grad():
+        up = TD.init_exact(UpsamplingAdd(128, 64), seed=3).eval()
+        x, skip = dense_input((3, 128, 9, 11), 2), dense_input((3, 64, 18, 22), 3)
+        ref = TD.upsampling_add(x.double(), skip.double(), f64(up))
+        y = up.to(DEV)(x.to(DEV), skip.to(DEV))
+    close(y, ref)
+
+
+@pytest.mark.parametrize("cin,cout", [(70, 64), (64, 64)])
+def test_temporal_block(cin, cout):
+    H, W = 20, 28
+    with torch.no_grad():
+        blk = TD.init_exact(TemporalBlock(cin, cout, use_pyramid_pooling=True, pool_sizes=[(2, H, W)]), seed=4).eval()
+        x = dense_input((2, cin, 3, H, W), 7)
+        ref = TD.temporal_block(x.double(), f64(blk))
+        y = blk.to(DEV)(x.to(DEV))
+    close(y, ref)
+
+
+def test_deeplab_head():
+    with torch.no_grad():
+        head = TD.init_exact(DeepLabHead(64, 64, hidden_channel=128), seed=5).eval()
+        x = dense_input((3, 64, 30, 44), 8)
+        ref = TD.deeplab_head(x.double(), f64(head))
+        y = head.to(DEV)(x.to(DEV))
+    close(y, ref)
+
+
+def _temporal_golden():
+    g = dict(np.load(os.path.join(GOLDEN, "dense_temporal_model.npz")))
+    x = dense_input((1, 3, 70, int(g["H"]), int(g["W"])), int(g["in_seed"]))
+    x[:, :, 64:] = x[:, :, 64:, :1, :1]
+    return g, x
+
+
+def test_temporal_model_vs_reference_golden_and_fp64():
+    g, x = _temporal_golden()
+    with torch.no_grad():
+        tm = TD.init_exact(TemporalModel(70, 3, (int(g["H"]), int(g["W"])), start_out_channels=64), seed=int(g["seed"])).eval()
+        ref64 = TD.temporal_model(x.double(), f64(tm))
+        y = tm.to(DEV)(x.to(DEV))
+    close(y, ref64)
+    close(y, torch.from_numpy(g["out"]))                  # the reference's own fp32 output
+
+
+def test_temporal_model_constant_channels_as_bias():
+    """The fused path never materialises the 6 broadcast ego-motion channels (stp3.py:145-152)."""
+    g, x = _temporal_golden()
+    with torch.no_grad():
+        tm = TD.init_exact(TemporalModel(70, 3, (int(g["H"]), int(g["W"])), start_out_channels=64), seed=int(g["seed"])).eval().to(DEV)
+        tm.model[0].n_const = 6
+        const = x[:, :, 64:, 0, 0].reshape(3, 6).contiguous().to(DEV)
+        y = dense.to_f32(tm.forward_hl(dense.from_f32(x[:, :, :64].to(DEV)), const=const), 0, 64)
+    close(y, torch.from_numpy(g["out"]))
+
+
+@pytest.mark.parametrize("name,gates", [("perceive", GATES_PERCEIVE), ("all", GATES_ALL)])
+def test_decoder_vs_reference_golden_and_fp64(name, gates):
+    g = dict(np.load(os.path.join(GOLDEN, f"dense_decoder_{name}.npz")))
+    x = dense_input((1, 3, 64, int(g["H"]), int(g["W"])), int(g["in_seed"]))
+    with torch.no_grad():
+        dec = TD.init_exact(Decoder(64, 2, 3, 2, gates), seed=int(g["seed"])).eval()
+        ref64 = TD.decoder(x.double(), f64(dec))
+        out = dec.to(DEV)(x.to(DEV))
+    for k, v in ref64.items():
+        if v is None:
+            assert out[k] is None
+            continue
+        assert out[k].shape == v.shape, (k, out[k].shape, v.shape)
+        close(out[k], v)
+        close(out[k], torch.from_numpy(g[k]))
+
+
+def test_decoder_batch2_full_resolution_shapes():
+    with torch.no_grad():
+        dec = TD.init_exact(Decoder(64, 2, 3, 2, GATES_PERCEIVE), seed=9).eval().to(DEV)
+        out = dec(dense_input((2, 3, 64, 200, 200), 10).to(DEV))
+    assert out["segmentation"].shape == (2, 3, 2, 200, 200) and out["hdmap"].shape == (2, 4, 200, 200)
+    assert all(torch.isfinite(v).all() for v in out.values() if v is not None)
+
+
+def test_training_mode_is_refused():
+    blk = TemporalBlock(64, 64).to(DEV)
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros(1, 64, 2, 8, 8, device=DEV))
