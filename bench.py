@@ -1,11 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — BEV frames/s of the ST-P3 camera->BEV hot path on B200.
+"""bench.py — BEV frames/s of the ST-P3 camera->BEV perception hot path on B200 (Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lift_splat|perceive] [--batch b_per_gpu]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload perceive|lift_splat] [--batch b_per_gpu]
   python bench.py --impl reference ...     # the reference's CPU path (oracle port) on the host cores
 
 One "step" = one pass of the hot path over one batch of synthetic samples (6 cameras x 3 frames, 200x200 BEV);
-one "frame" of the metric = one sample's BEV output.  Rank 0 prints ONE JSON line.
+one "frame" of the metric = one sample's BEV perception output.  Rank 0 prints ONE JSON line.
+
+  perceive   (default; BASELINE configs[3], the configuration the metric is quoted on): encoder outputs ->
+             lift-splat -> ego-motion + 3-D temporal block + DeepLab head -> BEV decoder heads (segmentation,
+             pedestrian, hdmap logits).  The EfficientNet trunk is third-party, absent from the image and excluded on
+             both arms: inputs enter as the trunk-head outputs (context features + depth logits).
+  lift_splat (BASELINE configs[2] lift stage): lift-splat only, output = (B,3,64,200,200) BEV features.
 """
 import argparse
 import json
@@ -26,6 +32,15 @@ from stp3_b200.utils import synthetic as syn  # noqa: E402
 
 METRIC = "bev_frames_per_sec"
 UNIT = "frames/s"
+# SURVEY.md §8d / BASELINE.md §3: 2*MAC, unpadded channels, counted on the reference modules
+GFLOP_TEMPORAL, GFLOP_DECODER = 134.7, 59.3
+WORKLOADS = {
+    "perceive": "perceive: 6 cam x 3 t x (28x60x48 frustum) -> lift-splat -> ego-warp + 3-D temporal block + DeepLab "
+                "head -> BEV decoder heads (seg/ped/hdmap), 200x200x64 BEV (BASELINE configs[3]; EfficientNet trunk "
+                "excluded on both arms)",
+    "lift_splat": "lift_splat: 6 cam x 3 t x (28x60x48 frustum) -> 200x200x64 BEV, ego-warp + discount "
+                  "(BASELINE configs[2] lift-splat stage)",
+}
 
 
 def algorithmic_bytes_lift_splat(cfg, batch):
@@ -103,45 +118,90 @@ def make_problem(cfg, batch, seed):
                 off=G.bev_offset(start, res))
 
 
+def build_model(device=None):
+    """Random-init (seeded, machine-independent) perception model; the trunk is not needed (inputs enter after it)."""
+    from stp3_b200.config import get_cfg
+    from stp3_b200.models.stp3 import STP3
+    cfg = get_cfg()
+    with torch.no_grad():
+        model = STP3(cfg, backbone=torch.nn.Identity())
+        geo = {k: getattr(model, k).detach().clone() for k in ("frustum", "bev_resolution", "bev_start_position", "bev_dimension")}
+        syn.init_exact(model, seed=0)
+        for k, v in geo.items():
+            getattr(model, k).copy_(v)
+    model.eval()
+    return model.to(device) if device is not None else model
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_step_lift_splat(cfg, prob):
-    """One sample through the op-for-op CPU port of the reference's lift-splat (oracle/torch_port.py)."""
+def reference_step(workload, cfg, prob, model):
+    """One sample through the CPU port of the reference's path (oracle/torch_port.py + oracle/torch_dense.py: the same
+    ATen operator sequence as the reference, which cannot travel to the GPU box)."""
     from oracle import torch_port as TP
     inp = prob["inp"]
     xs, ys, ds = prob["axes"]
     with torch.no_grad():
-        return TP.lift_splat(inp["feat"][:1], inp["depth_logits"][:1], inp["intrinsics"][:1], inp["extrinsics"][:1],
-                             inp["future_egomotion"][:1], xs, ys, ds, prob["res"], prob["start"], prob["dim"],
-                             cfg.discount)
+        bev = TP.lift_splat(inp["feat"][:1], inp["depth_logits"][:1], inp["intrinsics"][:1], inp["extrinsics"][:1],
+                            inp["future_egomotion"][:1], xs, ys, ds, prob["res"], prob["start"], prob["dim"],
+                            cfg.discount)
+        if workload == "lift_splat":
+            return bev
+        from oracle import torch_dense as TD
+        ego = inp["future_egomotion"][:1]
+        ego = torch.cat([torch.zeros_like(ego[:, :1]), ego[:, :-1]], 1)
+        x = torch.cat([bev, ego.view(1, -1, 6, 1, 1).expand(1, ego.shape[1], 6, *bev.shape[-2:])], dim=2)
+        return TD.decoder(TD.temporal_model(x, model.temporal_model), model.decoder)
 
 
-def time_reference(cfg, prob, steps, warmup):
+def pick_threads(cfg, prob):
+    """The eager CPU path is dominated by small ops and slows down when oversubscribed: give it its best thread count."""
+    from oracle import torch_port as TP
+    inp = prob["inp"]
+    xs, ys, ds = prob["axes"]
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    best, best_t = cores, float("inf")
+    for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        with torch.no_grad():   # one frame of one sample
+            TP.lift_splat(inp["feat"][:1, :1], inp["depth_logits"][:1, :1], inp["intrinsics"][:1, :1],
+                          inp["extrinsics"][:1, :1], inp["future_egomotion"][:1, :1], xs, ys, ds, prob["res"],
+                          prob["start"], prob["dim"], cfg.discount)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def time_reference(workload, cfg, steps, warmup):
+    prob = make_problem(cfg, 1, seed=0)
+    model = build_model() if workload == "perceive" else None
+    threads = pick_threads(cfg, prob)
     for _ in range(warmup):
-        reference_step_lift_splat(cfg, prob)
+        reference_step(workload, cfg, prob, model)
     t0 = time.perf_counter()
     for _ in range(steps):
-        reference_step_lift_splat(cfg, prob)
+        reference_step(workload, cfg, prob, model)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return 1.0 / dt, dt, cores
+    return 1.0 / dt, dt, threads
 
 
 def run_reference_arm(args, cfg):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    prob = make_problem(cfg, 1, seed=0)
-    steps = min(args.steps, 3)
-    warmup = min(args.warmup, 1)
-    fps, dt, cores = time_reference(cfg, prob, steps, warmup)
-    sample = f"1 sample (6 cam x {cfg.receptive_field} t) per step, {steps} timed step(s) after {warmup} warm-up"
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    fps, dt, threads = time_reference(args.workload, cfg, steps, warmup)
+    sample = (f"1 sample (6 cam x {cfg.receptive_field} t) per step, {steps} timed step(s) after {warmup} warm-up, "
+              f"{threads} of {os.cpu_count()} host threads (best of a short sweep)")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload_name, "batch_per_step": 1, "path": "oracle/torch_port.py (op-for-op CPU port of the reference; /root/reference cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS[args.workload], "batch_per_step": 1,
+                   "path": "oracle/torch_port.py + oracle/torch_dense.py: op-for-op CPU port of the reference "
+                           "(/root/reference is pure Python and cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -154,12 +214,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lift_splat", choices=["lift_splat"])
+    ap.add_argument("--workload", default="perceive", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step (perceive config 4: 32 / 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = syn.CONFIGS["perceive"]
-    args.workload_name = "lift_splat: 6 cam x 3 t x (28x60x48 frustum) -> 200x200x64 BEV, ego-warp + discount (BASELINE configs[2] lift-splat stage)"
 
     if args.impl == "reference":
         run_reference_arm(args, cfg)
@@ -176,29 +235,46 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     W, K, b = max(args.warmup, 3), args.steps, args.batch
+    perceive = args.workload == "perceive"
 
-    prob = make_problem(cfg, b, seed=rank)
+    prob = make_problem(cfg, b, seed=rank)          # every rank works on its own shard of the global batch
     inp = prob["inp"]
-    host = {k: inp[k].pin_memory() for k in ("feat", "depth_logits")}
+    host = {k: inp[k].pin_memory() for k in ("feat", "depth_logits", "intrinsics", "extrinsics", "future_egomotion")}
     host_mats = [m.pin_memory() for m in prob["mats"]]
     xs, ys, ds = (a.to(dev) for a in prob["axes"])
     d_feat, d_depth = host["feat"].to(dev), host["depth_logits"].to(dev)
     d_mats = [m.to(dev) for m in host_mats]
     X, Y = cfg.bev_xy
-    out = torch.empty((b, cfg.receptive_field, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
-    host_out = torch.empty(out.shape, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    model = build_model(dev) if perceive else None
+    if perceive:
+        host_out = {"segmentation": torch.empty((b, 3, 2, X, Y)).pin_memory(),
+                    "pedestrian": torch.empty((b, 3, 2, X, Y)).pin_memory(),
+                    "hdmap": torch.empty((b, 4, X, Y)).pin_memory()}
+    else:
+        out = torch.empty((b, cfg.receptive_field, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
+        host_out = {"bev": torch.empty(out.shape, dtype=torch.float32).pin_memory()}
 
     def step_resident():
-        ops.lift_splat(d_feat, d_depth, *d_mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount,
-                       out=out)
+        with torch.no_grad():
+            if perceive:
+                return model.forward_features(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+            ops.lift_splat(d_feat, d_depth, *d_mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
+            return {"bev": out}
 
     def step_e2e():
-        f = host["feat"].to(dev, non_blocking=True)
-        d = host["depth_logits"].to(dev, non_blocking=True)
-        mats = [m.to(dev, non_blocking=True) for m in host_mats]
-        ops.lift_splat(f, d, *mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
-        host_out.copy_(out, non_blocking=True)
+        """The call a user makes: host (pinned) inputs in, host results out."""
+        with torch.no_grad():
+            f = host["feat"].to(dev, non_blocking=True)
+            d = host["depth_logits"].to(dev, non_blocking=True)
+            if perceive:
+                res = model.forward_features(f, d, host["intrinsics"], host["extrinsics"], host["future_egomotion"])
+            else:
+                mats = [m.to(dev, non_blocking=True) for m in host_mats]
+                ops.lift_splat(f, d, *mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
+                res = {"bev": out}
+            for k, t in host_out.items():
+                t.copy_(res[k], non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -232,39 +308,77 @@ def main():
     e2e_ms = timed(step_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
 
+    # per-stage device time (CUDA events between the stages of forward_features), a few extra untimed steps
+    stage_ms = {}
+    if perceive:
+        n_prof = 5
+        for _ in range(n_prof):
+            model.stage_events = []
+            flush.zero_()
+            step_resident()
+            torch.cuda.synchronize()
+            ev = model.stage_events
+            for (_, a), (name, c) in zip(ev[:-1], ev[1:]):
+                stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(c) / n_prof
+        model.stage_events = None
+
     if rank == 0:
         ms_per_step = total_ms / K
         frames = b * world
         value = frames / (ms_per_step * 1e-3)
         pk = peaks()
         alg = algorithmic_bytes_lift_splat(cfg, b)
-        achieved = alg / (ms_per_step * 1e-3) / 1e9
-        h2d = sum(t.numel() * t.element_size() for t in list(host.values()) + host_mats)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("feat", "depth_logits"))
+        h2d += sum(t.numel() * t.element_size() for t in host_mats)
+        d2h = sum(t.numel() * 4 for t in host_out.values())
+        ls_ms = stage_ms.get("lift_splat", ms_per_step)
+        roof_ls = {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
+                   "achieved": alg / (ls_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": None,
+                   "algorithmic_bytes_per_step": alg, "ms": ls_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload_name, "samples_per_gpu_per_step": b, "global_batch": frames,
+            "dtype": "f32 (dense layers: bf16x3 split products, fp32 accumulate)" if perceive else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "samples_per_gpu_per_step": b, "global_batch": frames,
                        "cameras": cfg.n_cameras, "frames": cfg.receptive_field, "bev": [X, Y],
-                       "channels": cfg.out_channels, "depth_bins": cfg.n_depth, "parallelism": f"dp{world} (batch sharded, no collective)",
-                       "l2": "flushed between timed iterations (256 MiB write)"},
+                       "channels": cfg.out_channels, "depth_bins": cfg.n_depth,
+                       "parallelism": f"dp{world} (batch sharded, no collective on the forward path)",
+                       "l2": "flushed between timed iterations (256 MiB write)", "weights": "random init, seeded"},
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
-            "gpu_launches": 2 * K * 2,   # scatter + finalize kernels per step (no memset), resident and e2e timed regions
-            "roofline": {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
-                         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": None,
-                         "algorithmic_bytes_per_step": alg},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         }
+        if perceive:
+            dense_ms = stage_ms.get("temporal_model", 0.0) + stage_ms.get("decoder", 0.0)
+            flops = (GFLOP_TEMPORAL + GFLOP_DECODER) * 1e9 * b
+            ach = flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else None
+            line["stage_ms"] = stage_ms
+            line["gpu_launches"] = 2 * K * LAUNCHES_PER_PERCEIVE_STEP
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN> family (temporal model + decoder, 45 launches/step)",
+                                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
+                                "traffic": None, "algorithmic_flops_per_step": flops, "ms": dense_ms,
+                                "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
+            line["roofline_lift_splat"] = roof_ls
+        else:
+            line["gpu_launches"] = 2 * K * 2
+            line["roofline"] = roof_ls
         if world == 1 and not args.no_cpu_baseline:
-            fps, dt, cores = time_reference(cfg, make_problem(cfg, 1, seed=0), 1, 0)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "1 sample through oracle/torch_port.py (op-for-op CPU port of the reference lift-splat), 1 run"}
+            fps, dt, threads = time_reference(args.workload, cfg, 1, 0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"1 sample through the op-for-op CPU port of the reference (oracle/torch_port.py"
+                                              f"{' + oracle/torch_dense.py' if perceive else ''}), 1 run, {threads} threads"}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+# kernels of this repository launched by one perceive step: lift-splat 2, temporal blocks 2x(6 conv + 2 small),
+# DeepLab head 7 conv + 2, decoder 1 + 12 + 2 ds + 3 (1x1) + 3 upsample + heads 4, layout/aux ~6
+LAUNCHES_PER_PERCEIVE_STEP = 66
 
 
 if __name__ == "__main__":

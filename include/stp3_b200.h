@@ -153,11 +153,12 @@ int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int T, int C, 
 /* y[n][co] (+)= sum_ci W[co][ci] x[n][ci]: the 6 broadcast ego-motion channels of stp3.py:145-152 as a bias */
 int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, float* y, int co_stride, int accumulate,
                       void* stream);
-/* UpsamplingAdd tail (convolutions.py:204-215): y = bilinear_x2(x) + skip[..., s_coff:s_coff+C]; x is (n_img,h,w,.),
- * skip and y are (n_img,2h,2w,.) */
+/* y[..., y_coff:y_coff+C] = bilinear_x2(x[..., :C]) (+ skip[..., s_coff:s_coff+C] when skip is given); x is
+ * (n_img,h,w,.), skip and y are (n_img,2h,2w,.).  UpsamplingAdd tail (convolutions.py:204-215) and the upsample +
+ * concat of UpsamplingConcat (convolutions.py:183-201). */
 int stp3_upsample2x_add(const void* x_hi, const void* x_lo, int n_img, int h, int w, int x_cstride, const void* s_hi,
-                        const void* s_lo, int s_cstride, int s_coff, void* y_hi, void* y_lo, int y_cstride, int C,
-                        void* stream);
+                        const void* s_lo, int s_cstride, int s_coff, void* y_hi, void* y_lo, int y_cstride, int y_coff,
+                        int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,41 +17,12 @@ the reference, or fp64 for a tighter oracle).  Nothing here calls the modules' o
 Pinned by tests/test_dense_oracle.py: (a) in the build container against the reference modules' own forward on the
 same weights, (b) everywhere against tests/golden/dense_*.npz produced from the reference by oracle/make_golden.py.
 """
-import zlib
-
 import torch
 import torch.nn.functional as F
 
 
-# ------------------------------------------------------------------------------------------------ weights
-def exact_gauss(shape, gen):
-    s = torch.randint(0, 1 << 14, (4, *shape), generator=gen, dtype=torch.int32).sum(0)
-    return (s - (1 << 15)).float() / float(1 << 13)
-
-
-def init_exact(module, seed=0):
-    """Deterministic, machine-independent parameters/buffers keyed by state-dict name (integer RNG, power-of-two
-    scaling), so the build container (reference) and the GPU box (drop-in) hold bit-identical weights."""
-    sd = module.state_dict()
-    for name in sorted(sd):
-        t = sd[name]
-        gen = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
-        if name.endswith("num_batches_tracked"):
-            continue
-        if name.endswith("running_var"):
-            v = 0.5 + torch.randint(0, 1 << 14, t.shape, generator=gen).float() / float(1 << 14)
-        elif name.endswith("running_mean"):
-            v = exact_gauss(t.shape, gen) * 0.125
-        elif t.dim() == 1 and name.endswith("weight"):          # BatchNorm gamma
-            v = 1.0 + exact_gauss(t.shape, gen) * 0.125
-        elif t.dim() == 1:                                       # biases / BatchNorm beta
-            v = exact_gauss(t.shape, gen) * 0.125
-        else:                                                    # conv weights ~ N(0, 2/fan_in), power-of-two scale
-            fan_in = t[0].numel()
-            scale = 2.0 ** round(torch.log2(torch.tensor((2.0 / fan_in) ** 0.5 / 1.155)).item())
-            v = exact_gauss(t.shape, gen) * scale
-        t.copy_(v.to(t.dtype))
-    return module
+# seeded, machine-independent synthetic weights / inputs live with the other synthetic-data helpers
+from stp3_b200.utils.synthetic import exact_gauss, init_exact  # noqa: E402,F401
 
 
 # ------------------------------------------------------------------------------------------------ primitives
@@ -180,3 +151,21 @@ def decoder(x, dec):
     out['instance_flow'] = per_frame(_head(y, dec.instance_future_head)) if dec.predict_future_flow else None
     out['costvolume'] = per_frame(_head(y, dec.costvolume_head).squeeze(1)) if dec.planning else None
     return out
+
+
+def upsampling_concat(x_to_upsample, x, m):
+    """UpsamplingConcat (convolutions.py:183-201): upsample the coarse map x2, concat BEHIND the fine map, 2x conv."""
+    d = x.dtype
+    y = F.interpolate(x_to_upsample, scale_factor=2, mode='bilinear', align_corners=False)
+    y = torch.cat([x, y], dim=1)
+    y = F.relu(_bn(F.conv2d(y, m.conv[0].weight.to(d), padding=1), m.conv[1]))
+    return F.relu(_bn(F.conv2d(y, m.conv[3].weight.to(d), padding=1), m.conv[4]))
+
+
+def encoder_heads(r_lo, r_hi, enc):
+    """Encoder.get_features_depth after the trunk (encoder.py:88-95): r_lo (M,c3,H/8,W/8), r_hi (M,c4,H/16,W/16)."""
+    feat = upsampling_concat(deeplab_head(r_hi, enc.feature_layer_1), r_lo, enc.feature_layer_2)
+    depth = None
+    if enc.use_depth_distribution:
+        depth = upsampling_concat(deeplab_head(r_hi, enc.depth_layer_1), r_lo, enc.depth_layer_2)
+    return feat, depth

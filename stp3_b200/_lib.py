@@ -38,7 +38,7 @@ SIGNATURES = {
     "stp3_spatial_sum": (_I, [_V, _V, _I, _I, _I, _V, _V]),
     "stp3_pool_bias": (_I, [_V, _I, _I, _I, _I, _F, _I, _V, _V, _I, _V, _I, _V, _I, _I, _V]),
     "stp3_small_linear": (_I, [_V, _V, _I, _I, _I, _V, _I, _I, _V]),
-    "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _V]),
+    "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _V]),
     "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
                                  _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,

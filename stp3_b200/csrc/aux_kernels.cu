@@ -143,7 +143,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
 __global__ void __launch_bounds__(256)
 upsample2x_add_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int h, int w, int xs,
                       const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl, int ss, int s_off,
-                      __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int ys, int C8, size_t total) {
+                      __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int ys, int y_off, int C8,
+                      size_t total) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = idx % C8;
@@ -179,7 +180,7 @@ upsample2x_add_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16*
       }
     }
   const size_t opix = (img * H2 + oy) * W2 + ox;
-  {
+  if (sh != nullptr) {
     const size_t i = opix * ss + s_off + g * 8;
     const uint4 hv = *reinterpret_cast<const uint4*>(sh + i), lv = *reinterpret_cast<const uint4*>(sl + i);
     const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
@@ -198,8 +199,8 @@ upsample2x_add_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16*
     oh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
     ol[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
-  *reinterpret_cast<uint4*>(yh + opix * ys + g * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-  *reinterpret_cast<uint4*>(yl + opix * ys + g * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  *reinterpret_cast<uint4*>(yh + opix * ys + y_off + g * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+  *reinterpret_cast<uint4*>(yl + opix * ys + y_off + g * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
 }  // namespace stp3
@@ -258,14 +259,17 @@ extern "C" int stp3_small_linear(const float* x, const float* W, int n, int ci, 
 
 extern "C" int stp3_upsample2x_add(const void* x_hi, const void* x_lo, int n_img, int h, int w, int x_cstride,
                                    const void* s_hi, const void* s_lo, int s_cstride, int s_coff, void* y_hi, void* y_lo,
-                                   int y_cstride, int C, void* stream) {
-  STP3_CHECK_ARG(x_hi && x_lo && s_hi && s_lo && y_hi && y_lo && n_img > 0 && h > 0 && w > 0, "stp3_upsample2x_add: null/empty");
-  STP3_CHECK_ARG(C % 8 == 0 && C <= x_cstride && s_coff % 8 == 0 && s_coff + C <= s_cstride && C <= y_cstride &&
-                 x_cstride % 8 == 0 && s_cstride % 8 == 0 && y_cstride % 8 == 0, "stp3_upsample2x_add: channel windows must be multiples of 8");
+                                   int y_cstride, int y_coff, int C, void* stream) {
+  STP3_CHECK_ARG(x_hi && x_lo && y_hi && y_lo && n_img > 0 && h > 0 && w > 0, "stp3_upsample2x_add: null/empty");
+  STP3_CHECK_ARG((s_hi == nullptr) == (s_lo == nullptr), "stp3_upsample2x_add: give both skip planes or neither");
+  if (!s_hi) { s_cstride = 8; s_coff = 0; }
+  STP3_CHECK_ARG(C % 8 == 0 && C <= x_cstride && s_coff % 8 == 0 && (!s_hi || s_coff + C <= s_cstride) &&
+                 y_coff % 8 == 0 && y_coff + C <= y_cstride && x_cstride % 8 == 0 && s_cstride % 8 == 0 &&
+                 y_cstride % 8 == 0, "stp3_upsample2x_add: channel windows must be multiples of 8");
   const size_t total = (size_t)n_img * (2 * h) * (2 * w) * (C / 8);
   upsample2x_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x_hi, (const bf16*)x_lo, h, w, x_cstride, (const bf16*)s_hi, (const bf16*)s_lo, s_cstride, s_coff,
-      (bf16*)y_hi, (bf16*)y_lo, y_cstride, C / 8, total);
+      (bf16*)y_hi, (bf16*)y_lo, y_cstride, y_coff, C / 8, total);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }

@@ -240,14 +240,20 @@ def small_linear(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor, accumulate
     _lib.check(code, "stp3_small_linear")
 
 
-def upsample2x_add(x: HL, skip: HL, c: int, skip_coff: int = 0) -> HL:
-    """bilinear x2 (align_corners=False) of x plus skip[..., skip_coff:skip_coff+c]."""
+def upsample2x_add(x: HL, skip: Optional[HL], c: int, skip_coff: int = 0, out: Optional[HL] = None,
+                   out_coff: int = 0) -> HL:
+    """out[..., out_coff:out_coff+c] = bilinear x2 (align_corners=False) of x[..., :c] (+ skip[..., skip_coff:+c])."""
     B, T, h, w, xs = x.hi.shape
-    assert skip.hi.shape[:4] == (B, T, 2 * h, 2 * w)
-    out = HL.empty(B, T, 2 * h, 2 * w, c, x.hi.device, cp=c)
+    if skip is not None:
+        assert skip.hi.shape[:4] == (B, T, 2 * h, 2 * w)
+    if out is None:
+        out = HL.empty(B, T, 2 * h, 2 * w, c, x.hi.device, cp=c)
+    assert out.hi.shape[:4] == (B, T, 2 * h, 2 * w)
+    ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(x.hi.device):
-        code = _lib.lib().stp3_upsample2x_add(x.hi.data_ptr(), x.lo.data_ptr(), B * T, h, w, xs, skip.hi.data_ptr(),
-                                              skip.lo.data_ptr(), skip.hi.shape[-1], skip_coff, out.hi.data_ptr(),
-                                              out.lo.data_ptr(), c, c, _stream(x.hi.device))
+        code = _lib.lib().stp3_upsample2x_add(
+            x.hi.data_ptr(), x.lo.data_ptr(), B * T, h, w, xs, ptr(skip.hi if skip else None),
+            ptr(skip.lo if skip else None), skip.hi.shape[-1] if skip else 0, skip_coff, out.hi.data_ptr(),
+            out.lo.data_ptr(), out.hi.shape[-1], out_coff, c, _stream(x.hi.device))
     _lib.check(code, "stp3_upsample2x_add")
     return out

@@ -125,3 +125,43 @@ class DeepLabHead(nn.Sequential, PackedModule):
         """x (N,Cin,H,W) fp32 -> (N,num_classes,H,W) fp32."""
         y = self.forward_hl(dense.from_f32(x.unsqueeze(1)))
         return dense.to_f32(y, 0, self.num_classes).squeeze(1)
+
+
+class UpsamplingConcat(PackedModule):
+    """bilinear x2 of the coarse map, concat behind the fine map, two 3x3 conv/BN/ReLU (convolutions.py:183-201).
+    The upsample kernel writes straight into its channel window of the concat tensor."""
+
+    def __init__(self, in_channels, out_channels, scale_factor=2):
+        super().__init__()
+        assert scale_factor == 2
+        self.upsample = nn.Upsample(scale_factor=scale_factor, mode='bilinear', align_corners=False)
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        )
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+    def _pack(self):
+        w0, b0 = dense.fold_bn(self.conv[0].weight, self.conv[1])
+        w1, b1 = dense.fold_bn(self.conv[3].weight, self.conv[4])
+        return {"c0": (w0, b0), "c1": dense.pack_conv(w1, b1)}
+
+    def forward_hl(self, coarse: dense.HL, fine_f32: torch.Tensor) -> dense.HL:
+        """coarse: HL (B,1,h,w,.) with coarse.c real channels; fine_f32: (B, Cf, 2h, 2w) fp32."""
+        self._require_eval()
+        P = self.packed()
+        cf, cc = fine_f32.shape[1], coarse.c
+        assert cf + cc == self.in_channels and cf % 8 == 0 and cc % 8 == 0
+        key = ("c0p", cf, cc)
+        if key not in P:     # first conv packed for the physical layout [fine | coarse]
+            P[key] = dense.pack_conv(P["c0"][0], P["c0"][1], in_layout=[(0, cf, 0), (cf, cc, cf)])
+        cat = dense.from_f32(fine_f32.unsqueeze(1), cp=dense.pad_to(cf + cc))
+        dense.upsample2x_add(coarse, None, cc, out=cat, out_coff=cf)
+        y = dense.conv(cat, P[key], relu=True)
+        return dense.conv(y, P["c1"], relu=True)
+
+    def forward(self, x_to_upsample, x):
+        y = self.forward_hl(dense.from_f32(x_to_upsample.unsqueeze(1)), x)
+        return dense.to_f32(y, 0, self.out_channels).squeeze(1)

@@ -1,0 +1,173 @@
+"""STP3 perception model with the reference's constructor / forward surface (stp3/models/stp3.py:15-184) for the
+perception configuration (N_FUTURE_FRAMES = 0, PLANNING disabled): Encoder -> lift-splat -> TemporalModel -> Decoder,
+every stage on hand-written sm_100a kernels behind the C ABI.
+
+Device data flow of forward():
+    Encoder heads (tcgen05)  -> feature / depth-logit tensors
+    stp3_lift_splat_fwd      -> BEV grid directly as channels-last bf16 hi/lo planes + per-(b,t,c) spatial sums
+    TemporalModel (tcgen05)  -> ego-motion channels and pooling branches enter as per-image biases
+    Decoder (tcgen05)        -> fp32 logits in the reference's (B,S,k,X,Y) layout
+Prediction (N_FUTURE_FRAMES > 0) and planning are outside the hot path and are refused loudly.
+"""
+import torch
+import torch.nn as nn
+
+from .. import dense, ops
+from ..utils import geometry as G
+from .decoder import Decoder
+from .encoder import Encoder
+from .temporal_model import TemporalModel, TemporalModelIdentity
+
+
+class STP3(nn.Module):
+    def __init__(self, cfg, backbone=None):
+        super().__init__()
+        self.cfg = cfg
+        res, start, dim = G.calculate_birds_eye_view_parameters(cfg.LIFT.X_BOUND, cfg.LIFT.Y_BOUND, cfg.LIFT.Z_BOUND)
+        self.bev_resolution = nn.Parameter(res, requires_grad=False)
+        self.bev_start_position = nn.Parameter(start, requires_grad=False)
+        self.bev_dimension = nn.Parameter(dim, requires_grad=False)
+        self.encoder_downsample = cfg.MODEL.ENCODER.DOWNSAMPLE
+        self.encoder_out_channels = cfg.MODEL.ENCODER.OUT_CHANNELS
+        self.frustum = self.create_frustum()
+        self.depth_channels = self.frustum.shape[0]
+        self.discount = cfg.LIFT.DISCOUNT
+        if cfg.TIME_RECEPTIVE_FIELD == 1:
+            assert cfg.MODEL.TEMPORAL_MODEL.NAME == 'identity'
+        self.receptive_field = cfg.TIME_RECEPTIVE_FIELD
+        self.n_future = cfg.N_FUTURE_FRAMES
+        if self.n_future > 0 or cfg.PLANNING.ENABLED:
+            raise NotImplementedError("stp3_b200 implements the perception hot path (N_FUTURE_FRAMES=0, PLANNING "
+                                      "disabled); prediction / planning are out of scope (SURVEY.md §2, rows 12-13)")
+        self.spatial_extent = (cfg.LIFT.X_BOUND[1], cfg.LIFT.Y_BOUND[1])
+        self.bev_size = (int(dim[0]), int(dim[1]))
+
+        self.encoder = Encoder(cfg=cfg.MODEL.ENCODER, D=self.depth_channels, backbone=backbone)
+
+        temporal_in = self.encoder_out_channels + (6 if cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE else 0)
+        if cfg.MODEL.TEMPORAL_MODEL.NAME == 'identity':
+            self.temporal_model = TemporalModelIdentity(temporal_in, self.receptive_field)
+        elif cfg.MODEL.TEMPORAL_MODEL.NAME == 'temporal_block':
+            self.temporal_model = TemporalModel(
+                temporal_in, self.receptive_field, input_shape=self.bev_size,
+                start_out_channels=cfg.MODEL.TEMPORAL_MODEL.START_OUT_CHANNELS,
+                extra_in_channels=cfg.MODEL.TEMPORAL_MODEL.EXTRA_IN_CHANNELS,
+                n_spatial_layers_between_temporal_layers=cfg.MODEL.TEMPORAL_MODEL.INBETWEEN_LAYERS,
+                use_pyramid_pooling=cfg.MODEL.TEMPORAL_MODEL.PYRAMID_POOLING)
+            if cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE and len(self.temporal_model.model) > 0:
+                self.temporal_model.model[0].n_const = 6
+        else:
+            raise NotImplementedError(f'Temporal module {cfg.MODEL.TEMPORAL_MODEL.NAME}.')
+        self.future_pred_in_channels = self.temporal_model.out_channels
+
+        self.decoder = Decoder(
+            in_channels=self.future_pred_in_channels, n_classes=len(cfg.SEMANTIC_SEG.VEHICLE.WEIGHTS),
+            n_present=self.receptive_field, n_hdmap=len(cfg.SEMANTIC_SEG.HDMAP.ELEMENTS),
+            predict_gate={'perceive_hdmap': cfg.SEMANTIC_SEG.HDMAP.ENABLED,
+                          'predict_pedestrian': cfg.SEMANTIC_SEG.PEDESTRIAN.ENABLED,
+                          'predict_instance': cfg.INSTANCE_SEG.ENABLED,
+                          'predict_future_flow': cfg.INSTANCE_FLOW.ENABLED,
+                          'planning': cfg.PLANNING.ENABLED})
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+                m.momentum = cfg.MODEL.BN_MOMENTUM
+        self._ws = ops.Workspace()
+        self.stage_events = None        # bench.py sets this to a list to receive (stage name, CUDA event) marks
+
+    # ------------------------------------------------------------------------------------------------ geometry
+    def create_frustum(self):
+        """(D, Hf, Wf, 3) grid of (u, v, depth), kept as a parameter for state-dict compatibility (stp3.py:111-130);
+        the kernels only use its three 1-D axes."""
+        xs, ys, ds = G.frustum_axes(self.cfg.IMAGE.FINAL_DIM, self.encoder_downsample, self.cfg.LIFT.D_BOUND)
+        D, Hf, Wf = ds.numel(), ys.numel(), xs.numel()
+        fr = torch.stack((xs.view(1, 1, Wf).expand(D, Hf, Wf), ys.view(1, Hf, 1).expand(D, Hf, Wf),
+                          ds.view(D, 1, 1).expand(D, Hf, Wf)), -1)
+        return nn.Parameter(fr.contiguous(), requires_grad=False)
+
+    def _axes(self):
+        fr = self.frustum
+        return fr[0, 0, :, 0].contiguous(), fr[0, :, 0, 1].contiguous(), fr[:, 0, 0, 2].contiguous()
+
+    def _lift_args(self, intrinsics, extrinsics, future_egomotion):
+        cam_M, cam_t, ego_R, ego_t = G.lift_matrices(intrinsics, extrinsics, future_egomotion)
+        xs, ys, ds = self._axes()
+        off = G.bev_offset(self.bev_start_position, self.bev_resolution)
+        return (cam_M, cam_t, ego_R, ego_t, xs, ys, ds, off.detach().cpu(), self.bev_resolution.detach().cpu(),
+                self.bev_dimension.detach().cpu(), float(self.discount))
+
+    def projection_to_birds_eye_view(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        """(B,S,N,C,Hf,Wf) features + (B,S,N,D,Hf,Wf) depth logits -> (B,S,C,X,Y) fp32, as stp3.py:226-301 (which takes
+        the materialised outer product and geometry instead; both are fused away here)."""
+        return ops.lift_splat(feat, depth_logits, *self._lift_args(intrinsics, extrinsics, future_egomotion),
+                              use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, image, intrinsics, extrinsics, future_egomotion):
+        """image (B,T,N,3,H,W), intrinsics (B,T,N,3,3), extrinsics (B,T,N,4,4), future_egomotion (B,T,6) -> dict with
+        the reference's keys (stp3.py:132-184)."""
+        S = self.receptive_field
+        image = image[:, :S].contiguous()
+        b, s, n = image.shape[:3]
+        feat, depth = self.encoder(image.view(b * s * n, *image.shape[3:]))
+        feat = feat.view(b, s, n, *feat.shape[1:])
+        depth = depth.view(b, s, n, *depth.shape[1:]) if depth is not None else None
+        return self.forward_features(feat, depth, intrinsics, extrinsics, future_egomotion)
+
+    def forward_features(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        """Same as forward() but entering after the image encoder: feat (B,S,N,C,Hf,Wf), depth_logits
+        (B,S,N,D,Hf,Wf)."""
+        S = self.receptive_field
+        feat, intrinsics, extrinsics = feat[:, :S], intrinsics[:, :S].contiguous(), extrinsics[:, :S].contiguous()
+        depth_logits = depth_logits[:, :S] if depth_logits is not None else None
+        future_egomotion = future_egomotion[:, :S].contiguous()
+        B = feat.shape[0]
+        dev = feat.device
+        X, Y = self.bev_size
+        C = self.encoder_out_channels
+        output = {'depth_prediction': depth_logits, 'cam_front': None}
+
+        self._mark("start")
+        planes = torch.empty((2, B, S, X, Y, C), dtype=torch.bfloat16, device=dev)
+        use_pool = isinstance(self.temporal_model, TemporalModel) and len(self.temporal_model.model) > 0 and \
+            self.temporal_model.model[0].use_pyramid_pooling
+        res = ops.lift_splat(feat, depth_logits, *self._lift_args(intrinsics, extrinsics, future_egomotion),
+                             use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws,
+                             out_hilo=planes, pool_sum=use_pool)
+        sums = res[1].view(B * S, C) if use_pool else None
+        x = dense.HL(planes[0], planes[1], C)
+        self._mark("lift_splat")
+
+        if isinstance(self.temporal_model, TemporalModelIdentity):
+            bev = dense.to_f32(x, 0, C)
+            if self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE:
+                ego = self._shifted_egomotion(future_egomotion).view(B, S, 6, 1, 1).expand(B, S, 6, X, Y)
+                bev = torch.cat([bev, ego], dim=2)
+            states = dense.from_f32(bev)
+        else:
+            const = None
+            if self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE:
+                const = self._shifted_egomotion(future_egomotion).reshape(B * S, 6).contiguous().to(dev)
+            states = self.temporal_model.forward_hl(x, const=const, sums=sums)
+        self._mark("temporal_model")
+        output.update(self.decoder.forward_hl(states))
+        self._mark("decoder")
+        return output
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+
+    @staticmethod
+    def _shifted_egomotion(future_egomotion):
+        """stp3.py:148-151: frame t sees the ego-motion of frame t-1, frame 0 sees zeros."""
+        return torch.cat([torch.zeros_like(future_egomotion[:, :1]), future_egomotion[:, :-1]], dim=1).float()
+
+    def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics, future_egomotion):
+        """(B,S,N,3,H,W) images -> (bev (B,S,C,X,Y) fp32, depth logits (B,S,N,D,Hf,Wf), cam_front=None) (stp3.py:303-318)."""
+        b, s, n = x.shape[:3]
+        feat, depth = self.encoder(x.view(b * s * n, *x.shape[3:]))
+        feat = feat.view(b, s, n, *feat.shape[1:])
+        depth = depth.view(b, s, n, *depth.shape[1:]) if depth is not None else None
+        return self.projection_to_birds_eye_view(feat, depth, intrinsics, extrinsics, future_egomotion), depth, None

@@ -49,7 +49,8 @@ _default_ws = Workspace()
 def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
                discount: float, *, feat_channels_last: bool = False, out_channels_last: bool = False,
                use_depth_distribution: bool = True, return_ranks: bool = False, pool_sum: bool = False,
-               workspace: Optional[Workspace] = None, out: Optional[torch.Tensor] = None):
+               workspace: Optional[Workspace] = None, out: Optional[torch.Tensor] = None,
+               out_hilo: Optional[torch.Tensor] = None):
     """Fused lift (softmax-depth (x) context) + ego-aligned voxel pooling + temporal discount.
 
       feat          (B,S,N,C,Hf,Wf) or, with feat_channels_last, (B,S,N,Hf,Wf,C)
@@ -79,7 +80,11 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
     need = L.stp3_lift_splat_workspace_bytes(B, S, C, nx, ny)
     ws = (workspace or _default_ws).get(need, dev)
     oshape = (B, S, nx, ny, C) if out_channels_last else (B, S, C, nx, ny)
-    if out is None:
+    layout = int(out_channels_last)
+    if out_hilo is not None:      # two bf16 planes (2,B,S,nx,ny,C): the activation format of the tensor-core path
+        assert tuple(out_hilo.shape) == (2, B, S, nx, ny, C) and out_hilo.dtype == torch.bfloat16 and out_hilo.is_contiguous()
+        out, layout = out_hilo, 2
+    elif out is None:
         out = torch.empty(oshape, dtype=torch.float32, device=dev)
     else:
         assert tuple(out.shape) == oshape and out.is_contiguous() and out.dtype == torch.float32
@@ -93,7 +98,7 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
             xs.data_ptr(), ys.data_ptr(), ds.data_ptr(), _host3(bev_off), _host3(bev_res),
             nx, ny, nz, float(discount), B, S, N, D, Hf, Wf, C, int(use_depth_distribution),
             ranks.data_ptr() if ranks is not None else None, psum.data_ptr() if psum is not None else None,
-            ws.data_ptr(), ws.numel(), out.data_ptr(), int(out_channels_last), stream)
+            ws.data_ptr(), ws.numel(), out.data_ptr(), layout, stream)
     if code != 0:
         (workspace or _default_ws).reset()
     _lib.check(code, "stp3_lift_splat_fwd")

@@ -6,6 +6,7 @@ and Gaussian depth logits.  Everything is generated on the CPU with a fixed seed
 container (where the reference runs) and the GPU box see bit-identical tensors.
 """
 import math
+import zlib
 from dataclasses import dataclass, field
 from typing import Tuple
 
@@ -131,3 +132,30 @@ def lift_inputs(cfg: LiftSplatConfig, batch: int, seed: int = 0, focal_jitter=Tr
     ego = egomotion(cfg, batch, gen)
     return {"feat": feat, "depth_logits": depth, "intrinsics": intr, "extrinsics": extr,
             "future_egomotion": ego}
+
+
+def init_exact(module, seed=0):
+    """Deterministic, machine-independent parameters/buffers keyed by state-dict name (integer RNG, power-of-two
+    scaling): there are no checkpoints in the image, so benchmarks and parity tests run on seeded random weights,
+    and the build container (reference) and the GPU box (drop-in) must hold bit-identical values.  BatchNorm running
+    statistics are randomised so that the BN folding is exercised."""
+    sd = module.state_dict()
+    for name in sorted(sd):
+        t = sd[name]
+        gen = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+        if name.endswith("num_batches_tracked"):
+            continue
+        if name.endswith("running_var"):
+            v = 0.5 + torch.randint(0, 1 << 14, t.shape, generator=gen).float() / float(1 << 14)
+        elif name.endswith("running_mean"):
+            v = exact_gauss(t.shape, gen) * 0.125
+        elif t.dim() == 1 and name.endswith("weight"):          # BatchNorm gamma
+            v = 1.0 + exact_gauss(t.shape, gen) * 0.125
+        elif t.dim() == 1:                                       # biases / BatchNorm beta
+            v = exact_gauss(t.shape, gen) * 0.125
+        else:                                                    # conv weights ~ N(0, 2/fan_in), power-of-two scale
+            fan_in = t[0].numel()
+            scale = 2.0 ** round(math.log2((2.0 / fan_in) ** 0.5 / 1.155))
+            v = exact_gauss(t.shape, gen) * scale
+        t.copy_(v.to(t.dtype))
+    return module

@@ -135,3 +135,16 @@ def test_training_mode_is_refused():
     blk = TemporalBlock(64, 64).to(DEV)
     with pytest.raises(NotImplementedError):
         blk(torch.zeros(1, 64, 2, 8, 8, device=DEV))
+
+
+def test_encoder_heads_vs_reference_golden():
+    """DeepLabHead(160->160, hidden 64) + UpsamplingConcat(216->48): the depth head of the image encoder
+    (encoder.py:31-35, 88-95) against the output of the reference's own modules with the same weights."""
+    from stp3_b200.layers.convolutions import UpsamplingConcat
+    g = dict(np.load(os.path.join(GOLDEN, "dense_encoder_head.npz")))
+    with torch.no_grad():
+        h = TD.init_exact(DeepLabHead(160, 160, hidden_channel=64), seed=11).eval().to(DEV)
+        u = TD.init_exact(UpsamplingConcat(216, 48), seed=12).eval().to(DEV)
+        r_hi, r_lo = dense_input((2, 160, 14, 30), 21).to(DEV), dense_input((2, 56, 28, 60), 22).to(DEV)
+        y = u(h(r_hi), r_lo)
+    close(y, torch.from_numpy(g["out"]))

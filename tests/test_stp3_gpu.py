@@ -1,0 +1,88 @@
+"""GPU: the assembled drop-in STP3 (perception configuration) end to end against the composed oracle
+(numpy lift-splat in fp64 -> torch fp64 TemporalModel -> torch fp64 Decoder) with identical weights and inputs."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lift_splat_oracle as O
+from oracle import torch_dense as TD
+from stp3_b200.config import get_cfg
+from stp3_b200.models.stp3 import STP3
+from stp3_b200.utils import geometry as G
+from stp3_b200.utils import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class FakeTrunk(torch.nn.Module):
+    """Stands in for the third-party EfficientNet trunk (absent from the image): deterministic endpoints."""
+
+    def forward(self, x):
+        m = x.shape[0]
+        g = torch.Generator().manual_seed(3)
+        h, w = x.shape[-2] // 8, x.shape[-1] // 8
+        r3 = TD.exact_gauss((m, 56, h, w), g).to(x.device)
+        r4 = TD.exact_gauss((m, 160, h // 2, w // 2), g).to(x.device)
+        return r3, r4
+
+
+def small_cfg():
+    return get_cfg({"LIFT": {"X_BOUND": [-8.0, 8.0, 0.5], "Y_BOUND": [-8.0, 8.0, 0.5], "D_BOUND": [2.0, 10.0, 1.0]},
+                    "IMAGE": {"FINAL_DIM": (32, 48)}})
+
+
+def test_forward_features_matches_composed_oracle():
+    cfg = small_cfg()
+    lcfg = syn.LiftSplatConfig(x_bound=(-8.0, 8.0, 0.5), y_bound=(-8.0, 8.0, 0.5), d_bound=(2.0, 10.0, 1.0),
+                               final_dim=(32, 48), out_channels=64, n_cameras=2, receptive_field=3)
+    inp = syn.lift_inputs(lcfg, 2, seed=4, random_pose=True)
+    with torch.no_grad():
+        model = TD.init_exact(STP3(cfg, backbone=FakeTrunk()), seed=7).eval()
+        # init_exact also rewrote the geometry buffers: restore them
+        model.frustum.copy_(model.create_frustum()); 
+        res, start, dim = G.calculate_birds_eye_view_parameters(cfg.LIFT.X_BOUND, cfg.LIFT.Y_BOUND, cfg.LIFT.Z_BOUND)
+        model.bev_resolution.copy_(res); model.bev_start_position.copy_(start); model.bev_dimension.copy_(dim)
+        ref_model = copy.deepcopy(model).double()
+        model = model.to(DEV)
+        out = model.forward_features(inp["feat"].to(DEV), inp["depth_logits"].to(DEV), inp["intrinsics"],
+                                     inp["extrinsics"], inp["future_egomotion"])
+        # ---- oracle
+        cam_M, cam_t, ego_R, ego_t = G.lift_matrices(inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+        xs, ys, ds = G.frustum_axes(cfg.IMAGE.FINAL_DIM, 8, cfg.LIFT.D_BOUND)
+        bev = O.lift_splat(inp["feat"].numpy(), inp["depth_logits"].numpy(), cam_M.numpy(), cam_t.numpy(), ego_R.numpy(),
+                           ego_t.numpy(), xs.numpy(), ys.numpy(), ds.numpy(), G.bev_offset(start, res).numpy(),
+                           res.numpy(), dim.numpy(), cfg.LIFT.DISCOUNT)["bev"]
+        x = torch.from_numpy(bev)                                            # (B,S,64,X,Y) fp64
+        ego = inp["future_egomotion"].double()
+        ego = torch.cat([torch.zeros_like(ego[:, :1]), ego[:, :-1]], 1)      # stp3.py:148-151
+        x = torch.cat([x, ego.view(2, 3, 6, 1, 1).expand(2, 3, 6, *x.shape[-2:])], dim=2)
+        states = TD.temporal_model(x, ref_model.temporal_model)
+        ref = TD.decoder(states, ref_model.decoder)
+    assert out["depth_prediction"].shape == inp["depth_logits"].shape and out["cam_front"] is None
+    for k in ("segmentation", "pedestrian", "hdmap"):
+        r = ref[k]
+        err = (out[k].double().cpu() - r).abs().max().item()
+        assert out[k].shape == r.shape
+        assert err <= 1e-3 * r.abs().max().item(), (k, err, r.abs().max().item())      # north_star: logits within 1e-3
+    for k in ("instance_center", "instance_offset", "instance_flow", "costvolume"):
+        assert out[k] is None
+
+
+def test_forward_from_images_runs_with_injected_trunk():
+    cfg = small_cfg()
+    with torch.no_grad():
+        model = STP3(cfg, backbone=FakeTrunk()).eval().to(DEV)
+        lcfg = syn.LiftSplatConfig(x_bound=(-8.0, 8.0, 0.5), y_bound=(-8.0, 8.0, 0.5), d_bound=(2.0, 10.0, 1.0),
+                                   final_dim=(32, 48), out_channels=64, n_cameras=2, receptive_field=3)
+        inp = syn.lift_inputs(lcfg, 1, seed=5)
+        image = torch.zeros(1, 3, 2, 3, 32, 48, device=DEV)
+        out = model(image, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+        bev, depth, cam_front = model.calculate_birds_eye_view_features(image, inp["intrinsics"], inp["extrinsics"],
+                                                                        inp["future_egomotion"])
+    assert out["segmentation"].shape == (1, 3, 2, 32, 32) and out["hdmap"].shape == (1, 4, 32, 32)
+    assert out["depth_prediction"].shape == (1, 3, 2, 8, 4, 6)
+    assert bev.shape == (1, 3, 64, 32, 32) and depth.shape == (1, 3, 2, 8, 4, 6) and cam_front is None
+    assert all(torch.isfinite(v).all() for v in out.values() if v is not None)
