@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--workload", default="perceive", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step (perceive config 4: 32 / 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     cfg = syn.CONFIGS["perceive"]
 
@@ -247,6 +248,11 @@ def main():
     X, Y = cfg.bev_xy
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     model = build_model(dev) if perceive else None
+    graphed = None
+    if perceive and not args.no_graph:
+        from stp3_b200.models.stp3 import GraphedPerception
+        graphed = GraphedPerception(model, b, cfg.n_cameras, dev)
+        graphed(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])   # fill the static inputs
     if perceive:
         host_out = {"segmentation": torch.empty((b, 3, 2, X, Y)).pin_memory(),
                     "pedestrian": torch.empty((b, 3, 2, X, Y)).pin_memory(),
@@ -257,6 +263,9 @@ def main():
 
     def step_resident():
         with torch.no_grad():
+            if graphed is not None:
+                graphed.graph.replay()            # inputs already resident in the graph's static buffers
+                return graphed.out
             if perceive:
                 return model.forward_features(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
             ops.lift_splat(d_feat, d_depth, *d_mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
@@ -265,11 +274,16 @@ def main():
     def step_e2e():
         """The call a user makes: host (pinned) inputs in, host results out."""
         with torch.no_grad():
-            f = host["feat"].to(dev, non_blocking=True)
-            d = host["depth_logits"].to(dev, non_blocking=True)
-            if perceive:
+            if graphed is not None:
+                res = graphed(host["feat"], host["depth_logits"], host["intrinsics"], host["extrinsics"],
+                              host["future_egomotion"])
+            elif perceive:
+                f = host["feat"].to(dev, non_blocking=True)
+                d = host["depth_logits"].to(dev, non_blocking=True)
                 res = model.forward_features(f, d, host["intrinsics"], host["extrinsics"], host["future_egomotion"])
             else:
+                f = host["feat"].to(dev, non_blocking=True)
+                d = host["depth_logits"].to(dev, non_blocking=True)
                 mats = [m.to(dev, non_blocking=True) for m in host_mats]
                 ops.lift_splat(f, d, *mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
                 res = {"bev": out}
@@ -308,19 +322,10 @@ def main():
     e2e_ms = timed(step_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-stage device time (CUDA events between the stages of forward_features), a few extra untimed steps
+    # per-stage device time: each stage captured as its own CUDA graph (no launch gaps), timed with CUDA events
     stage_ms = {}
     if perceive:
-        n_prof = 5
-        for _ in range(n_prof):
-            model.stage_events = []
-            flush.zero_()
-            step_resident()
-            torch.cuda.synchronize()
-            ev = model.stage_events
-            for (_, a), (name, c) in zip(ev[:-1], ev[1:]):
-                stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(c) / n_prof
-        model.stage_events = None
+        stage_ms = time_stages(model, graphed.static if graphed is not None else None, d_feat, d_depth, inp, flush, dev)
 
     if rank == 0:
         ms_per_step = total_ms / K
@@ -374,6 +379,56 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
+    """GPU time of the three stages of STP3.forward_device, each replayed as its own CUDA graph."""
+    from stp3_b200 import dense, ops
+    from stp3_b200.models.stp3 import STP3  # noqa: F401
+    if static is None:
+        h = {k: v.to(dev) for k, v in model.prepare_inputs(inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"]).items()}
+        static = dict(feat=d_feat, depth_logits=d_depth, **h)
+    B, S = static["feat"].shape[:2]
+    X, Y = model.bev_size
+    C = model.encoder_out_channels
+    off, res, dim = model._bev_host()
+    planes = torch.empty((2, B, S, X, Y, C), dtype=torch.bfloat16, device=dev)
+    hold = {}
+
+    def lift():
+        r = ops.lift_splat(static["feat"], static["depth_logits"], static["cam_M"], static["cam_t"], static["ego_R"],
+                           static["ego_t"], *model._axes(), off, res, dim, float(model.discount), workspace=model._ws,
+                           out_hilo=planes, pool_sum=True)
+        hold["sums"] = r[1].view(B * S, C)
+
+    def temporal():
+        hold["states"] = model.temporal_model.forward_hl(dense.HL(planes[0], planes[1], C), const=static["const"],
+                                                         sums=hold["sums"])
+
+    def decoder():
+        hold["out"] = model.decoder.forward_hl(hold["states"])
+
+    out = {}
+    with torch.no_grad():
+        for name, fn in (("lift_splat", lift), ("temporal_model", temporal), ("decoder", decoder)):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); g.replay(); c.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(c)
+            out[name] = tot / reps
+    return out
 
 
 # kernels of this repository launched by one perceive step: lift-splat 2, temporal blocks 2x(6 conv + 2 small),

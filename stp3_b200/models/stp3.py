@@ -88,17 +88,33 @@ class STP3(nn.Module):
         fr = self.frustum
         return fr[0, 0, :, 0].contiguous(), fr[0, :, 0, 1].contiguous(), fr[:, 0, 0, 2].contiguous()
 
-    def _lift_args(self, intrinsics, extrinsics, future_egomotion):
-        cam_M, cam_t, ego_R, ego_t = G.lift_matrices(intrinsics, extrinsics, future_egomotion)
-        xs, ys, ds = self._axes()
-        off = G.bev_offset(self.bev_start_position, self.bev_resolution)
-        return (cam_M, cam_t, ego_R, ego_t, xs, ys, ds, off.detach().cpu(), self.bev_resolution.detach().cpu(),
-                self.bev_dimension.detach().cpu(), float(self.discount))
+    def _bev_host(self):
+        """(offset, resolution, dimension) as host values, evaluated once with the reference's fp32 tensor expression."""
+        cached = self.__dict__.get("_bev_host_cache")
+        if cached is None:
+            res, start, dim = (t.detach().cpu() for t in (self.bev_resolution, self.bev_start_position, self.bev_dimension))
+            cached = (G.bev_offset(start, res), res, dim)
+            self.__dict__["_bev_host_cache"] = cached
+        return cached
+
+    def prepare_inputs(self, intrinsics, extrinsics, future_egomotion):
+        """Host-side parameters of one batch, computed with the reference's own torch calls: camera
+        matrices R.K^-1 | t, ego poses R | t, and the shifted ego-motion vector that replaces the six broadcast
+        channels of stp3.py:145-152.  Small CPU tensors (a few hundred floats)."""
+        S = self.receptive_field
+        intrinsics, extrinsics = intrinsics[:, :S].float().cpu(), extrinsics[:, :S].float().cpu()
+        ego = future_egomotion[:, :S].float().cpu().contiguous()
+        cam_M, cam_t, ego_R, ego_t = G.lift_matrices(intrinsics, extrinsics, ego)
+        const = self._shifted_egomotion(ego).reshape(-1, 6).contiguous()
+        return {"cam_M": cam_M, "cam_t": cam_t, "ego_R": ego_R, "ego_t": ego_t, "const": const}
 
     def projection_to_birds_eye_view(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
         """(B,S,N,C,Hf,Wf) features + (B,S,N,D,Hf,Wf) depth logits -> (B,S,C,X,Y) fp32, as stp3.py:226-301 (which takes
         the materialised outer product and geometry instead; both are fused away here)."""
-        return ops.lift_splat(feat, depth_logits, *self._lift_args(intrinsics, extrinsics, future_egomotion),
+        h = self.prepare_inputs(intrinsics, extrinsics, future_egomotion)
+        off, res, dim = self._bev_host()
+        return ops.lift_splat(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(), off, res,
+                              dim, float(self.discount),
                               use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws)
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -117,37 +133,41 @@ class STP3(nn.Module):
         """Same as forward() but entering after the image encoder: feat (B,S,N,C,Hf,Wf), depth_logits
         (B,S,N,D,Hf,Wf)."""
         S = self.receptive_field
-        feat, intrinsics, extrinsics = feat[:, :S], intrinsics[:, :S].contiguous(), extrinsics[:, :S].contiguous()
-        depth_logits = depth_logits[:, :S] if depth_logits is not None else None
-        future_egomotion = future_egomotion[:, :S].contiguous()
-        B = feat.shape[0]
+        dev = feat.device
+        h = {k: v.to(dev) for k, v in self.prepare_inputs(intrinsics, extrinsics, future_egomotion).items()}
+        feat = feat[:, :S].contiguous()
+        depth_logits = depth_logits[:, :S].contiguous() if depth_logits is not None else None
+        return self.forward_device(feat, depth_logits, **h)
+
+    def forward_device(self, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, const):
+        """Device-only part of the forward pass (every argument already on the GPU; no host synchronisation, so the
+        whole call can be captured in a CUDA graph -- see GraphedPerception)."""
+        B, S = feat.shape[:2]
         dev = feat.device
         X, Y = self.bev_size
         C = self.encoder_out_channels
+        off, res, dim = self._bev_host()
         output = {'depth_prediction': depth_logits, 'cam_front': None}
 
         self._mark("start")
         planes = torch.empty((2, B, S, X, Y, C), dtype=torch.bfloat16, device=dev)
         use_pool = isinstance(self.temporal_model, TemporalModel) and len(self.temporal_model.model) > 0 and \
             self.temporal_model.model[0].use_pyramid_pooling
-        res = ops.lift_splat(feat, depth_logits, *self._lift_args(intrinsics, extrinsics, future_egomotion),
-                             use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws,
-                             out_hilo=planes, pool_sum=use_pool)
-        sums = res[1].view(B * S, C) if use_pool else None
+        r = ops.lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, *self._axes(), off, res, dim,
+                           float(self.discount), use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
+                           workspace=self._ws, out_hilo=planes, pool_sum=use_pool)
+        sums = r[1].view(B * S, C) if use_pool else None
         x = dense.HL(planes[0], planes[1], C)
         self._mark("lift_splat")
 
+        use_ego = self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE
         if isinstance(self.temporal_model, TemporalModelIdentity):
             bev = dense.to_f32(x, 0, C)
-            if self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE:
-                ego = self._shifted_egomotion(future_egomotion).view(B, S, 6, 1, 1).expand(B, S, 6, X, Y)
-                bev = torch.cat([bev, ego], dim=2)
+            if use_ego:
+                bev = torch.cat([bev, const.view(B, S, 6, 1, 1).expand(B, S, 6, X, Y)], dim=2)
             states = dense.from_f32(bev)
         else:
-            const = None
-            if self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE:
-                const = self._shifted_egomotion(future_egomotion).reshape(B * S, 6).contiguous().to(dev)
-            states = self.temporal_model.forward_hl(x, const=const, sums=sums)
+            states = self.temporal_model.forward_hl(x, const=const if use_ego else None, sums=sums)
         self._mark("temporal_model")
         output.update(self.decoder.forward_hl(states))
         self._mark("decoder")
@@ -171,3 +191,52 @@ class STP3(nn.Module):
         feat = feat.view(b, s, n, *feat.shape[1:])
         depth = depth.view(b, s, n, *depth.shape[1:]) if depth is not None else None
         return self.projection_to_birds_eye_view(feat, depth, intrinsics, extrinsics, future_egomotion), depth, None
+
+
+class GraphedPerception:
+    """STP3.forward_features for a fixed batch size replayed as ONE CUDA graph: the ~70 kernel launches of a step
+    (lift-splat, tcgen05 convolutions, helpers) are captured once -- tensor maps and kernel arguments are baked in, all
+    buffers are static -- so a step costs one graph launch instead of ~70 Python/ctypes launches.
+
+        g = GraphedPerception(model, batch)
+        out = g(feat, depth_logits, intrinsics, extrinsics, future_egomotion)   # host or device tensors
+    The returned tensors are the graph's static output buffers (overwritten by the next call)."""
+
+    def __init__(self, model: STP3, batch: int, n_cameras: int, device=None):
+        self.model = model
+        dev = torch.device(device) if device is not None else next(model.parameters()).device
+        S, C, D = model.receptive_field, model.encoder_out_channels, model.depth_channels
+        Hf, Wf = model.frustum.shape[1:3]
+        N = n_cameras
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.static = {
+            "feat": torch.zeros((batch, S, N, C, Hf, Wf), **f32),
+            "depth_logits": torch.zeros((batch, S, N, D, Hf, Wf), **f32),
+            "cam_M": torch.zeros((batch, S, N, 3, 3), **f32), "cam_t": torch.zeros((batch, S, N, 3), **f32),
+            "ego_R": torch.zeros((batch, S, 3, 3), **f32), "ego_t": torch.zeros((batch, S, 3), **f32),
+            "const": torch.zeros((batch * S, 6), **f32),
+        }
+        self.pinned = {k: torch.zeros(v.shape, dtype=torch.float32).pin_memory()
+                       for k, v in self.static.items() if k not in ("feat", "depth_logits")}
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up: weight packing, workspace allocation, lazy init
+                    model.forward_device(**self.static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = model.forward_device(**self.static)
+
+    def __call__(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        host = self.model.prepare_inputs(intrinsics, extrinsics, future_egomotion)
+        for k, v in host.items():
+            self.pinned[k].copy_(v)
+            self.static[k].copy_(self.pinned[k], non_blocking=True)
+        S = self.model.receptive_field
+        self.static["feat"].copy_(feat[:, :S], non_blocking=True)
+        self.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
+        self.graph.replay()
+        return self.out
