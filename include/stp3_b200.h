@@ -62,7 +62,7 @@ const char* stp3_last_error(void);
  *                 out_layout==2: two bf16 planes [2][B,S,nx,ny,C] (hi then lo; C % 8 == 0): the activation format
  *                                of the tensor-core path, consumed directly by stp3_conv_fwd
  *   pool_sum      optional (B,S,C) fp32: sum over the nx*ny cells of out[b,t,c] (feeds the pyramid-pooling branch
- *                 of TemporalBlock, temporal.py:408-423); must be zero-initialised by the caller.
+ *                 of TemporalBlock, temporal.py:408-423); fully overwritten by the call.
  *   workspace     >= stp3_lift_splat_workspace_bytes(...) bytes, 256-byte aligned.  It holds the channels-last
  *                 fp32 scatter grid (B,S,nx*ny,C) and a per-pillar occupancy map.  It must be ALL ZERO on entry:
  *                 clear it once with stp3_lift_splat_workspace_init() after allocating it; every successful
@@ -126,9 +126,24 @@ typedef struct stp3_conv_desc {
   int sigmoid;           /* apply a sigmoid to y_f32 (instance_center head, decoder.py:70) */
 } stp3_conv_desc;
 
+/* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:
+ *   out_k[img, y, x] = b[k] + sum_c w[k][c] * y[img, y, x, c]      (k < n_out <= 8; sigmoid where the mask bit is set)
+ * This is the 3x3 conv -> BN -> ReLU -> 1x1 conv(+bias) tail of every decoder head (decoder.py:38-89); several heads
+ * that share their input run as ONE convolution (their 3x3 kernels concatenated along N) and each head's 1x1 weights
+ * occupy its column block of w.  out[k] points at the (Ho, Wo) fp32 plane of output k for image 0 and consecutive
+ * images are img_stride[k] elements apart, so every head writes its own contiguous (n_img, k_out, Ho, Wo) tensor. */
+typedef struct stp3_conv_head {
+  int n_out;
+  const float* w;          /* [n_out][bn] fp32 (device) */
+  const float* b;          /* [n_out] fp32 (device) */
+  float* out[8];
+  long long img_stride[8];
+  int sigmoid_mask;
+} stp3_conv_head;
+
 int stp3_conv_fwd(const stp3_conv_desc* desc, const void* x_hi, const void* x_lo, const void* w, const float* bias,
                   const float* img_bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
-                  float* y_f32, void* stream);
+                  float* y_f32, const stp3_conv_head* head /* may be NULL */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Memory-bound helpers of the dense path (all tensors channels-last bf16 hi/lo planes unless noted).

@@ -27,6 +27,12 @@ class ConvDesc(ctypes.Structure):
                 ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I)]
 
 
+class ConvHead(ctypes.Structure):
+    """Mirror of stp3_conv_head (include/stp3_b200.h)."""
+    _fields_ = [("n_out", _I), ("w", _V), ("b", _V), ("out", _V * 8), ("img_stride", ctypes.c_longlong * 8),
+                ("sigmoid_mask", _I)]
+
+
 SIGNATURES = {
     "stp3_abi_version": (_I, []),
     "stp3_build_info": (ctypes.c_char_p, []),
@@ -39,7 +45,7 @@ SIGNATURES = {
     "stp3_pool_bias": (_I, [_V, _I, _I, _I, _I, _F, _I, _V, _V, _I, _V, _I, _V, _I, _I, _V]),
     "stp3_small_linear": (_I, [_V, _V, _I, _I, _I, _V, _I, _I, _V]),
     "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _V]),
-    "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, ctypes.POINTER(ConvHead), _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,
                                  _I, _I, _I, _F, _I, _I, _I, _I, _I, _I, _I, _I,
                                  _V, _V, _V, _SZ, _V, _I, _V]),

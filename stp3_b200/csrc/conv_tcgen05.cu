@@ -19,6 +19,8 @@
 // Reference layers: stp3/layers/temporal.py:252-489, stp3/layers/convolutions.py:183-280, stp3/models/decoder.py.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -50,30 +52,43 @@ struct ConvParams {
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
   int n_valid;
   int sigmoid;              // apply to out_f32 (instance_center head)
+  int n_stages;             // smem ring depth chosen by the host (1 .. kMaxStages)
+  // fused 1x1 "head" on the activated tile: out_k = head_b[k] + sum_c head_w[k][c] * y[c]  (decoder heads 3x3 -> 1x1)
+  int head_ko;              // 0 = off, else 1..8 outputs
+  const float* head_w;      // [head_ko][BN]
+  const float* head_b;      // [head_ko]
+  float* head_out[8];       // plane of output k for image 0 (fp32, (Ho, Wo))
+  long long head_img_stride[8];   // elements between consecutive images for output k
+  int head_sigmoid_mask;    // bit k: sigmoid on output k
 };
+
+constexpr int kMaxStages = 8;
+constexpr int kMaxHeadOut = 8;
 
 template <int BN>
 struct ConvSmem {
   static constexpr int kStageBytes = 2 * 128 * kBK * 2 + 2 * BN * kBK * 2;
-  static constexpr int kStages = (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr size_t kBytes = 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + 2 * BN * sizeof(float) + 256;
+  static constexpr size_t tail_bytes() { return (2 + kMaxHeadOut) * BN * sizeof(float) + (2 * kMaxStages + 2) * 8; }
+  static constexpr size_t bytes(int stages) { return 1024 /*alignment slack*/ + (size_t)stages * kStageBytes + tail_bytes(); }
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using S = ConvSmem<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stage_base = smem;
-  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S::kStages * S::kStageBytes);   // [2][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * BN);
-  uint64_t* full_bar = bars;                      // [kStages]
-  uint64_t* empty_bar = bars + S::kStages;        // [kStages]
-  uint64_t* tmem_full_bar = bars + 2 * S::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+  const int n_stages = p.n_stages;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)n_stages * S::kStageBytes);   // [2][BN]
+  float* s_head = s_bias + 2 * BN;                // [kMaxHeadOut][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_head + kMaxHeadOut * BN);
+  uint64_t* full_bar = bars;                      // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;        // [kMaxStages]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = blockIdx.x;
@@ -86,7 +101,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
-    for (int i = 0; i < S::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < n_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -95,6 +110,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     s_bias[i] = p.bias[i];
     s_bias[BN + i] = p.img_bias ? p.img_bias[(size_t)img * BN + i] : 0.f;
   }
+  for (int i = threadIdx.x; i < p.head_ko * BN; i += blockDim.x) s_head[i] = p.head_w[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -121,7 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int wrow = (it * 2) * BN;            // [tap][kb][plane][BN] rows of 64
         ptx::tma_load_2d(sb_hi, &tm_w, &full_bar[stage], 0, wrow);
         ptx::tma_load_2d(sb_lo, &tm_w, &full_bar[stage], 0, wrow + BN);
-        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -147,7 +163,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
         if (it == k_iters - 1) ptx::umma_commit(tmem_full_bar);
-        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -157,22 +173,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int oy = oy0 + (r >> 4), ox = ox0 + (r & 15);
     const bool valid = oy < p.Ho && ox < p.Wo;
     const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+    float hacc[kMaxHeadOut];
+#pragma unroll
+    for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
 #pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      uint32_t acc[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, acc);
+    for (int j = 0; j < BN / 16; ++j) {
+      uint32_t acc[16];
+      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + j * 16, acc);
       ptx::tmem_ld_wait();
       if (valid) {
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[j * 32 + i] + s_bias[BN + j * 32 + i];
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[j * 16 + i] + s_bias[BN + j * 16 + i];
         if (p.res_mode) {
-          const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + j * 32);
-          const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + j * 32);
+          const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + j * 16);
+          const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + j * 16);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
@@ -186,14 +205,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           }
         } else if (p.relu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (p.out_hi) {
-          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + j * 32);
-          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + j * 32);
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + j * 16);
+          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + j * 16);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (j * 32 + g * 8 >= p.n_store) break;
+          for (int g = 0; g < 2; ++g) {
+            if (j * 16 + g * 8 >= p.n_store) break;
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -210,14 +229,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         if (p.out_f32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = j * 32 + i;
+          for (int i = 0; i < 16; ++i) {
+            const int c = j * 16 + i;
             if (c < p.n_valid) {
               float x = v[i];
               if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
               p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
             }
           }
+        }
+        if (p.head_ko) {
+#pragma unroll
+          for (int k = 0; k < kMaxHeadOut; ++k) {
+            if (k < p.head_ko) {
+              const float* w = s_head + k * BN + j * 16;
+              float a = hacc[k];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) a = fmaf(w[i], v[i], a);
+              hacc[k] = a;
+            }
+          }
+        }
+      }
+    }
+    if (p.head_ko && valid) {
+#pragma unroll
+      for (int k = 0; k < kMaxHeadOut; ++k) {
+        if (k < p.head_ko) {
+          float x = hacc[k] + p.head_b[k];
+          if (p.head_sigmoid_mask & (1 << k)) x = 1.f / (1.f + __expf(-x));
+          p.head_out[k][(size_t)img * p.head_img_stride[k] + (size_t)oy * p.Wo + ox] = x;
         }
       }
     }
@@ -250,10 +291,14 @@ using namespace stp3;
 
 extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w,
                              const float* bias, const float* img_bias, const void* res_hi, const void* res_lo,
-                             void* y_hi, void* y_lo, float* y_f32, void* stream_) {
+                             void* y_hi, void* y_lo, float* y_f32, const stp3_conv_head* head, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   STP3_CHECK_ARG(d && x_hi && x_lo && w && bias, "stp3_conv_fwd: null pointer argument");
-  STP3_CHECK_ARG((y_hi && y_lo) || y_f32, "stp3_conv_fwd: no output tensor");
+  STP3_CHECK_ARG((y_hi && y_lo) || y_f32 || head, "stp3_conv_fwd: no output tensor");
+  if (head) {
+    STP3_CHECK_ARG(head->n_out >= 1 && head->n_out <= kMaxHeadOut && head->w && head->b, "bad fused head");
+    for (int k = 0; k < head->n_out; ++k) STP3_CHECK_ARG(head->out[k] != nullptr, "fused head: null output plane");
+  }
   STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "non-positive dimension");
   const int T_total = d->T_total > 0 ? d->T_total : d->T;
   STP3_CHECK_ARG(d->t0 >= 0 && d->t0 + d->T <= T_total, "frame window [t0, t0+T) outside the input tensor");
@@ -314,14 +359,37 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
   p.out_cstride = d->out_cstride; p.out_coff = d->out_coff; p.n_store = n_store;
   p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
+  p.head_ko = 0; p.head_w = nullptr; p.head_b = nullptr; p.head_sigmoid_mask = 0;
+  for (int k = 0; k < kMaxHeadOut; ++k) { p.head_out[k] = nullptr; p.head_img_stride[k] = 0; }
+  if (head) {
+    p.head_ko = head->n_out; p.head_w = head->w; p.head_b = head->b; p.head_sigmoid_mask = head->sigmoid_mask;
+    for (int k = 0; k < head->n_out; ++k) { p.head_out[k] = head->out[k]; p.head_img_stride[k] = head->img_stride[k]; }
+  }
+  // smem ring depth: no deeper than the K loop, and shallow enough that two CTAs share an SM (their load, MMA and
+  // epilogue phases then overlap; a single-tile CTA has no other way to hide its epilogue)
+  const int k_iters = d->ntaps * kblocks;
 
   const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;
   STP3_CHECK_ARG(nblk > 0 && nblk < (1ll << 31), "grid too large");
+  // policy 0 (default): shallow ring + 2 CTAs/SM for short K loops and for BN=64; BN=128 with a long K loop keeps
+  // a 3-deep ring on one CTA.  policy 1: always favour 2 CTAs/SM.  (STP3_CONV_POLICY, for A/B measurements.)
+  static const int policy = [] { const char* e = getenv("STP3_CONV_POLICY"); return e ? atoi(e) : 0; }();
 #define STP3_LAUNCH_CONV(BN_)                                                                                     \
   do {                                                                                                            \
+    const int max_st = BN_ == 64 ? 4 : (BN_ == 128 ? 3 : 2);                                                      \
+    const int budget = 112 * 1024; /* per CTA, so that two fit in 227 KB */                                       \
+    int st = (int)((budget - 1024 - ConvSmem<BN_>::tail_bytes()) / ConvSmem<BN_>::kStageBytes);                   \
+    if (st < 1) st = 1;                                                                                           \
+    if (BN_ == 256) st = 2;        /* 96 KB stages: one CTA per SM, two stages */                                  \
+    if (BN_ == 128 && k_iters > 2 && policy == 0) st = 3;                                                         \
+    if (policy == 2) st = max_st;  /* one CTA per SM, deepest ring (the v1 behaviour) */                          \
+    if (st > k_iters) st = k_iters;                                                                               \
+    if (st > max_st) st = max_st;                                                                                 \
+    p.n_stages = st;                                                                                              \
+    const size_t smem_bytes = ConvSmem<BN_>::bytes(st);                                                           \
     STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      (int)ConvSmem<BN_>::kBytes));                                               \
-    conv_igemm_kernel<BN_><<<(unsigned)nblk, kConvThreads, ConvSmem<BN_>::kBytes, stream>>>(tm_hi, tm_lo, tm_w, p); \
+                                      (int)ConvSmem<BN_>::bytes(max_st)));                                        \
+    conv_igemm_kernel<BN_><<<(unsigned)nblk, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);          \
   } while (0)
   if (d->bn == 64) STP3_LAUNCH_CONV(64);
   else if (d->bn == 128) STP3_LAUNCH_CONV(128);

@@ -413,13 +413,13 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
             if (VEC || c0 + i < C) __stcs(out + (bt * C + c0 + i) * (size_t)nvox + pcell, acc[i]);
         }
       }
-      if (pool_sum) {                      // per-(b,t,c) spatial sum for the pyramid-pooling branch
+      if (pool_sum) {    // per-(b,t,c) spatial sum for the pyramid-pooling branch: one partial per CTA, no atomics
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float s = acc[i];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0 && c0 + i < C) atomicAdd(pool_sum + bt * C + c0 + i, s);
+          if (lane == 0 && c0 + i < C) pool_sum[(((size_t)b * gridDim.x + blockIdx.x) * S + t) * C + c0 + i] = s;
         }
       }
     }
@@ -449,6 +449,27 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
   }
 }
 
+// pool_sum[b,t,c] = sum over the finalize CTAs' partials (B, nblk, S, C); grid (B*S), block (32, 8)
+__global__ void pool_reduce_kernel(const float* __restrict__ part, int nblk, int S, int C, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int b = blockIdx.x / S, t = blockIdx.x % S;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + threadIdx.x;
+    float a = 0.f;
+    if (c < C)
+      for (int k = threadIdx.y; k < nblk; k += 8) a += part[(((size_t)b * nblk + k) * S + t) * C + c];
+    sm[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      float tot = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) tot += sm[r][threadIdx.x];
+      out[(size_t)blockIdx.x * C + c] = tot;
+    }
+    __syncthreads();
+  }
+}
+
 // C > 64 only: occupancy bytes are cleared after every channel group has consumed them
 __global__ void clear_bytes_kernel(unsigned char* __restrict__ p, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,10 +485,12 @@ static size_t grid_bytes(int B, int S, int C, int nx, int ny) {
   return (g + 255) & ~(size_t)255;
 }
 
+static size_t occ_bytes(int B, int S, int nx, int ny) { return ((size_t)B * S * nx * ny + 255) & ~(size_t)255; }
+
 extern "C" size_t stp3_lift_splat_workspace_bytes(int B, int S, int C, int nx, int ny) {
   if (B <= 0 || S <= 0 || C <= 0 || nx <= 0 || ny <= 0) return 0;
-  const size_t o = ((size_t)B * S * nx * ny + 255) & ~(size_t)255;
-  return grid_bytes(B, S, C, nx, ny) + o;
+  const size_t part = (((size_t)B * ceil_div(nx * ny, 32) * S * C * sizeof(float)) + 255) & ~(size_t)255;
+  return grid_bytes(B, S, C, nx, ny) + occ_bytes(B, S, nx, ny) + part;   // scatter grid | occupancy | pool partials
 }
 
 extern "C" int stp3_lift_splat_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
@@ -547,12 +570,17 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   const int nvox = nx * ny * nz;
   const int groups = ceil_div(C, 64);                 // 8 warps x 8 channels per CTA
   dim3 fgrid(ceil_div(nvox, 32), B, groups), fblock(32, C >= 64 ? 8 : ceil_div(C, 8));
+  float* pool_part = pool_sum ? reinterpret_cast<float*>(p.occ + occ_bytes(B, S, nx, ny)) : nullptr;
 #define STP3_FINALIZE(VEC, SMAX) \
-  bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_sum, S, C, nvox, discount, out_layout)
+  bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_part, S, C, nvox, discount, out_layout)
   if (C % 8 == 0) { if (S <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
   else            { if (S <= 4) STP3_FINALIZE(false, 4); else STP3_FINALIZE(false, 8); }
 #undef STP3_FINALIZE
   STP3_CUDA_OK(cudaGetLastError());
+  if (pool_sum) {
+    pool_reduce_kernel<<<B * S, dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), S, C, pool_sum);
+    STP3_CUDA_OK(cudaGetLastError());
+  }
   if (groups > 1) {
     const size_t nocc = ((size_t)B * S * nvox + 255) & ~(size_t)255;
     clear_bytes_kernel<<<(unsigned)((nocc / 16 + 255) / 256), 256, 0, stream>>>(p.occ, nocc);

@@ -127,8 +127,8 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
 def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, out_coff: int = 0, relu: bool = False,
          img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
-         out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None
-         ) -> Optional[HL]:
+         out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
+         head: Optional[dict] = None, store: bool = True) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias + img_bias [+ residual]) written into out[..., out_coff:...]."""
     B, T_total, H, W, cs = x.hi.shape
     t0, T = frames if frames is not None else (0, T_total)      # process frames [t0, t0+T) of every sample
@@ -142,8 +142,20 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
     for i, (dt, dy, dx) in enumerate(pc.taps):
         d.taps[i][0], d.taps[i][1], d.taps[i][2] = dt, dy, dx
     d.bn = pc.bn
-    if out is None and out_f32 is None:
+    if out is None and out_f32 is None and store:
         out = HL.empty(B, T, Ho, Wo, pc.cout, x.hi.device, cp=pc.bn)
+    hd = None
+    if head is not None:
+        # fused 1x1 head: dict(w (KO,bn) f32, b (KO) f32, outs=[(tensor (n_img,k,Ho,Wo) f32, channel)], sigmoid_mask)
+        hd = _lib.ConvHead()
+        hd.n_out = len(head["outs"])
+        assert head["w"].shape == (hd.n_out, pc.bn) and head["w"].is_contiguous() and head["b"].numel() == hd.n_out
+        hd.w, hd.b = head["w"].data_ptr(), head["b"].data_ptr()
+        for k, (t, ch) in enumerate(head["outs"]):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == B * T and t.shape[2:] == (Ho, Wo)
+            hd.out[k] = t.data_ptr() + ch * Ho * Wo * 4
+            hd.img_stride[k] = t.shape[1] * Ho * Wo
+        hd.sigmoid_mask = int(head.get("sigmoid_mask", 0))
     if out is not None:
         assert out.hi.shape[:4] == (B, T, Ho, Wo), (out.hi.shape, (B, T, Ho, Wo))
         d.out_cstride, d.out_coff, d.n_store = out.hi.shape[-1], out_coff, n_store
@@ -162,7 +174,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
             ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), ptr(img_bias),
             ptr(residual.hi if residual is not None else None), ptr(residual.lo if residual is not None else None),
             ptr(out.hi if out is not None else None), ptr(out.lo if out is not None else None), ptr(out_f32),
-            torch.cuda.current_stream(dev).cuda_stream)
+            ctypes.byref(hd) if hd is not None else None, torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(code, "stp3_conv_fwd")
     return out
 

@@ -74,29 +74,42 @@ class Decoder(PackedModule):
                 if blk.downsample is not None:
                     w, b = dense.fold_bn(blk.downsample[0].weight, blk.downsample[1])
                     P[f"{name}.{i}.ds"] = dense.pack_conv(w, b, stride=blk.downsample[0].stride[0])
-        # heads: the 3x3 convolutions of all all-frame heads share the input -> fused along N in groups of <= 256
+        # heads: the 3x3 convolutions of the all-frame heads share their input -> concatenated along N in groups of
+        # <= 256 columns; every head's 1x1 conv(+bias, +sigmoid) is evaluated in the epilogue of that convolution
         c = self.in_channels
+        cp = dense.pad_to(c)
         all_frames = [(k, getattr(self, attr)) for k, attr, present in self._HEADS if hasattr(self, attr) and not present]
-        groups = []
-        per = max(1, 256 // dense.pad_to(c))
+        groups, per = [], max(1, 256 // cp)
         for i in range(0, len(all_frames), per):
-            grp = all_frames[i:i + per]
-            ws, bs = zip(*[dense.fold_bn(h[0].weight, h[1]) for _, h in grp])
-            cp = dense.pad_to(c)
-            wcat = torch.zeros(len(grp) * cp, c, 3, 3, device=ws[0].device)
-            bcat = torch.zeros(len(grp) * cp, device=ws[0].device)
-            for j, (w_, b_) in enumerate(zip(ws, bs)):
-                wcat[j * cp:j * cp + c], bcat[j * cp:j * cp + c] = w_, b_
-            groups.append((dense.pack_conv(wcat, bcat, bn=dense.out_tile(len(grp) * cp)),
-                           [(k, dense.pack_conv(h[3].weight.detach().float(), h[3].bias.detach().float()),
-                             h[3].out_channels, len(h) > 4) for k, h in grp]))
+            groups.append(self._pack_head_group(all_frames[i:i + per], c, cp))
         P["head_groups"] = groups
         if self.perceive_hdmap:
-            h = self.hdmap_head
-            w, b = dense.fold_bn(h[0].weight, h[1])
-            P["hdmap3"] = dense.pack_conv(w, b)
-            P["hdmap1"] = dense.pack_conv(h[3].weight.detach().float(), h[3].bias.detach().float())
+            P["hdmap"] = self._pack_head_group([("hdmap", self.hdmap_head)], c, cp)
         return P
+
+    @staticmethod
+    def _pack_head_group(grp, c, cp):
+        dev = grp[0][1][0].weight.device
+        bn = dense.out_tile(len(grp) * cp)
+        wcat = torch.zeros(len(grp) * cp, c, 3, 3, device=dev)
+        bcat = torch.zeros(len(grp) * cp, device=dev)
+        n_out = sum(h[3].out_channels for _, h in grp)
+        assert n_out <= 8
+        w2 = torch.zeros(n_out, bn, device=dev)
+        b2 = torch.zeros(n_out, device=dev)
+        members, k, mask = [], 0, 0
+        for j, (key, h) in enumerate(grp):
+            w_, b_ = dense.fold_bn(h[0].weight, h[1])
+            wcat[j * cp:j * cp + c], bcat[j * cp:j * cp + c] = w_, b_
+            ko = h[3].out_channels
+            w2[k:k + ko, j * cp:j * cp + c] = h[3].weight.detach().float().reshape(ko, c)
+            b2[k:k + ko] = h[3].bias.detach().float()
+            if len(h) > 4:                       # nn.Sigmoid tail (instance_center head)
+                mask |= ((1 << ko) - 1) << k
+            members.append((key, ko))
+            k += ko
+        return {"conv": dense.pack_conv(wcat, bcat, bn=bn), "w2": w2.contiguous(), "b2": b2.contiguous(),
+                "members": members, "mask": mask}
 
     def _basic_block(self, x, P, key, has_ds):
         y = dense.conv(x, P[f"{key}.c1"], relu=True)
@@ -123,19 +136,22 @@ class Decoder(PackedModule):
         y = self.up1_skip.forward_hl(y, skip1)
 
         out = {k: None for k, _, _ in self._HEADS}
-        cp = dense.pad_to(self.in_channels)
-        for pc3, members in P["head_groups"]:
-            hid = dense.conv(y, pc3, relu=True)
-            for j, (key, pc1, k_out, sig) in enumerate(members):
-                o = torch.empty((B * S, k_out, H, W), dtype=torch.float32, device=dev)
-                dense.conv(hid, pc1, cin_off=j * cp, out_f32=o, n_valid=k_out, sigmoid=sig)
-                out[key] = o.view(B, S, k_out, H, W)
+
+        def run_group(G, frames, n_img):
+            outs, tensors = [], {}
+            for key, ko in G["members"]:
+                t = torch.empty((n_img, ko, H, W), dtype=torch.float32, device=dev)
+                tensors[key] = t
+                outs += [(t, ch) for ch in range(ko)]
+            dense.conv(y, G["conv"], relu=True, frames=frames, store=False,
+                       head={"w": G["w2"], "b": G["b2"], "outs": outs, "sigmoid_mask": G["mask"]})
+            return tensors
+
+        for G in P["head_groups"]:
+            for key, t in run_group(G, None, B * S).items():
+                out[key] = t.view(B, S, t.shape[1], H, W)
         if self.perceive_hdmap:
-            hid = dense.conv(y, P["hdmap3"], relu=True, frames=(self.n_present - 1, 1))
-            k_out = self.hdmap_head[3].out_channels
-            o = torch.empty((B, k_out, H, W), dtype=torch.float32, device=dev)
-            dense.conv(hid, P["hdmap1"], out_f32=o, n_valid=k_out)
-            out["hdmap"] = o
+            out["hdmap"] = run_group(P["hdmap"], (self.n_present - 1, 1), B)["hdmap"]
         if out["costvolume"] is not None:
             out["costvolume"] = out["costvolume"].squeeze(2)
         return out

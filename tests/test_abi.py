@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_workspace_query_and_argument_errors():
     L = _lib.lib()
-    assert L.stp3_lift_splat_workspace_bytes(1, 3, 64, 200, 200) == 3 * 64 * 200 * 200 * 4 + ((3 * 200 * 200 + 255) // 256) * 256
+    assert L.stp3_lift_splat_workspace_bytes(1, 3, 64, 200, 200) == 3 * 64 * 200 * 200 * 4 + ((3 * 200 * 200 + 255) // 256) * 256 + 1250 * 3 * 64 * 4
     assert L.stp3_lift_splat_workspace_bytes(0, 3, 64, 200, 200) == 0
     # null pointers are rejected before anything touches the GPU
     import ctypes

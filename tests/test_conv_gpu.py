@@ -117,3 +117,25 @@ def test_channel_window_input():
     pc = dense.pack_conv(w.to(DEV), b.to(DEV))
     y = dense.conv(to_hl(x), pc, cin_off=64)
     check(from_hl(y), ref_conv2d(x[:, :, 64:], w, b))
+
+
+def test_fused_head_epilogue():
+    """3x3 conv -> BN(folded) -> ReLU -> 1x1 conv(+bias) of two decoder heads evaluated in one launch (decoder.py:38-52):
+    the hidden tensor is never stored; each head writes its own contiguous fp32 NCHW tensor."""
+    B, T, C, H, W = 1, 2, 64, 18, 22
+    x = rnd(B, T, C, H, W, seed=20)
+    w3 = rnd(128, C, 3, 3, seed=21, scale=0.05)          # two heads' 3x3 kernels concatenated along N
+    b3 = rnd(128, seed=22)
+    w1a, b1a = rnd(2, 64, seed=23, scale=0.2), rnd(2, seed=24)
+    w1b, b1b = rnd(1, 64, seed=25, scale=0.2), rnd(1, seed=26)
+    pc = dense.pack_conv(w3.to(DEV), b3.to(DEV))
+    w2 = torch.zeros(3, 128); w2[:2, :64] = w1a; w2[2:, 64:] = w1b
+    oa = torch.empty(B * T, 2, H, W, device=DEV); ob = torch.empty(B * T, 1, H, W, device=DEV)
+    dense.conv(to_hl(x), pc, relu=True, store=False,
+               head={"w": w2.to(DEV).contiguous(), "b": torch.cat([b1a, b1b]).to(DEV), "outs": [(oa, 0), (oa, 1), (ob, 0)],
+                     "sigmoid_mask": 0b100})
+    hid = F.relu(ref_conv2d(x, w3, b3)).view(B * T, 128, H, W)
+    ra = F.conv2d(hid[:, :64], w1a.double().view(2, 64, 1, 1), b1a.double())
+    rb = torch.sigmoid(F.conv2d(hid[:, 64:], w1b.double().view(1, 64, 1, 1), b1b.double()))
+    check(oa.cpu(), ra)
+    check(ob.cpu(), rb, tol=1e-5)
