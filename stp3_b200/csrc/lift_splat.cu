@@ -450,14 +450,19 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
 }
 
 // pool_sum[b,t,c] = sum over the finalize CTAs' partials (B, nblk, S, C); grid (B*S), block (32, 8)
-__global__ void pool_reduce_kernel(const float* __restrict__ part, int nblk, int S, int C, float* __restrict__ out) {
+// (the partials are zeroed again after they are read: the whole workspace stays all-zero between calls)
+__global__ void pool_reduce_kernel(float* __restrict__ part, int nblk, int S, int C, float* __restrict__ out) {
   __shared__ float sm[8][33];
   const int b = blockIdx.x / S, t = blockIdx.x % S;
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + threadIdx.x;
     float a = 0.f;
     if (c < C)
-      for (int k = threadIdx.y; k < nblk; k += 8) a += part[(((size_t)b * nblk + k) * S + t) * C + c];
+      for (int k = threadIdx.y; k < nblk; k += 8) {
+        float* src = part + (((size_t)b * nblk + k) * S + t) * C + c;
+        a += *src;
+        *src = 0.f;
+      }
     sm[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {

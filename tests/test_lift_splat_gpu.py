@@ -147,3 +147,16 @@ def test_workspace_is_left_clean_and_reusable():
     b = run_cuda(cfg, inp, g, workspace=ws)
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
     assert int(ws.buf.count_nonzero()) == 0
+
+
+def test_workspace_clean_after_pool_sum_call_of_another_shape():
+    """Regression: a call that emits pool sums must leave the shared workspace all-zero too (its per-CTA partials
+    live in the workspace), otherwise a later call with a different shape would scatter into dirty memory."""
+    ws = ops.Workspace()
+    cfg, inp, g = load_lift_case("plumbing")
+    run_cuda(cfg, inp, g, workspace=ws, pool_sum=True)
+    torch.cuda.synchronize()
+    assert int(ws.buf.count_nonzero()) == 0
+    cfg2, inp2, g2 = load_lift_case("tiny_randpose")
+    out = run_cuda(cfg2, inp2, g2, workspace=ws)
+    assert_bev_close(out.cpu().numpy(), run_oracle(cfg2, inp2, g2)["bev"])
