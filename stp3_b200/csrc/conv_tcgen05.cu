@@ -371,9 +371,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 
   const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;
   STP3_CHECK_ARG(nblk > 0 && nblk < (1ll << 31), "grid too large");
-  // policy 0 (default): shallow ring + 2 CTAs/SM for short K loops and for BN=64; BN=128 with a long K loop keeps
-  // a 3-deep ring on one CTA.  policy 1: always favour 2 CTAs/SM.  (STP3_CONV_POLICY, for A/B measurements.)
-  static const int policy = [] { const char* e = getenv("STP3_CONV_POLICY"); return e ? atoi(e) : 0; }();
+  // policy 1 (default, measured fastest): always favour 2 CTAs/SM.  policy 0: BN=128 with a long K loop keeps
+  // a 3-deep ring on one CTA.  policy 2: one CTA/SM, deepest ring.  (STP3_CONV_POLICY, for A/B measurements.)
+  static const int policy = [] { const char* e = getenv("STP3_CONV_POLICY"); return e ? atoi(e) : 1; }();
 #define STP3_LAUNCH_CONV(BN_)                                                                                     \
   do {                                                                                                            \
     const int max_st = BN_ == 64 ? 4 : (BN_ == 128 ? 3 : 2);                                                      \
