@@ -204,7 +204,7 @@ def run_reference_arm(args, cfg):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -234,6 +234,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     W, K, b = max(args.warmup, 3), args.steps, args.batch
     perceive = args.workload == "perceive"
@@ -375,7 +377,7 @@ def main():
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 sample through the op-for-op CPU port of the reference (oracle/torch_port.py"
                                               f"{' + oracle/torch_dense.py' if perceive else ''}), 1 run, {threads} threads"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
