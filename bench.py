@@ -292,10 +292,10 @@ def main():
             for k, t in host_out.items():
                 t.copy_(res[k], non_blocking=True)
 
+    from stp3_b200 import parallel
+
     def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps):
@@ -305,13 +305,7 @@ def main():
             flush.zero_()                      # evict L2 between timed iterations (not timed)
             s.record(); fn(); e.record()
         barrier()
-        total_ms = sum(s.elapsed_time(e) for s, e in evs)
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
+        return parallel.max_over_ranks(sum(s.elapsed_time(e) for s, e in evs), dev)
 
     for _ in range(W):
         step_resident()
