@@ -11,10 +11,13 @@
 // folded into the weights/bias on the host; bias, per-image bias (pyramid-pool / ASPP-pool / ego-motion
 // branches), ReLU, residual add and the concat offset are fused in the epilogue.
 //
-//   CTA tile : 128 output pixels (8 rows x 16 columns of one image) x BN output channels (64 / 128 / 256)
+//   tile     : 128 output pixels (8 rows x 16 columns of one image) x BN output channels (64 / 128 / 256)
 //   K loop   : taps x (Cin / 64); per step TMA brings A_hi, A_lo (128x64 bf16, 128B-swizzled) and B_hi, B_lo
-//              (BN x 64) and one thread issues 4 (UMMA_K=16) x 3 tcgen05.mma
-//   warps    : 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM -> regs -> global)
+//              (BN x 64; small weight tensors stay resident in smem) and one thread issues 4 (UMMA_K=16) x 3
+//              tcgen05.mma into one of TWO TMEM accumulator buffers
+//   CTA      : persistent, one per SM, walks tiles blockIdx.x + i*gridDim.x through one smem ring
+//   warps    : 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (TMEM -> regs -> global), which
+//              drains accumulator i while the tensor pipe fills accumulator i^1
 //
 // Reference layers: stp3/layers/temporal.py:252-489, stp3/layers/convolutions.py:183-280, stp3/models/decoder.py.
 #include <cuda_bf16.h>
@@ -26,14 +29,18 @@
 
 namespace stp3 {
 
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter, each owning half of the columns
+constexpr int kConvThreads = 64 + kEpiWarps * 32;
 constexpr int kTileH = 8, kTileW = 16;          // 128 output pixels = UMMA M
 constexpr int kBK = 64;                         // channels per K step (one 128-byte swizzle row of bf16)
 constexpr int kMaxTaps = 49;
+constexpr int kMaxStages = 8;
+constexpr int kMaxHeadOut = 8;
+constexpr int kAStageBytes = 2 * 128 * kBK * 2; // A_hi + A_lo tiles of one K step
 
 struct ConvParams {
   int n_img, T, t0, Ho, Wo;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, n_tiles;
   int stride;
   int kblocks;              // Cin / 64 of this convolution
   int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
@@ -52,7 +59,8 @@ struct ConvParams {
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
   int n_valid;
   int sigmoid;              // apply to out_f32 (instance_center head)
-  int n_stages;             // smem ring depth chosen by the host (1 .. kMaxStages)
+  int n_stages;             // smem ring depth chosen by the host (2 .. kMaxStages)
+  int b_resident;           // all weight tiles of the convolution stay in shared memory for the CTA's lifetime
   // fused 1x1 "head" on the activated tile: out_k = head_b[k] + sum_c head_w[k][c] * y[c]  (decoder heads 3x3 -> 1x1)
   int head_ko;              // 0 = off, else 1..8 outputs
   const float* head_w;      // [head_ko][BN]
@@ -62,205 +70,261 @@ struct ConvParams {
   int head_sigmoid_mask;    // bit k: sigmoid on output k
 };
 
-constexpr int kMaxStages = 8;
-constexpr int kMaxHeadOut = 8;
-
 template <int BN>
 struct ConvSmem {
-  static constexpr int kStageBytes = 2 * 128 * kBK * 2 + 2 * BN * kBK * 2;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr size_t tail_bytes() { return (2 + kMaxHeadOut) * BN * sizeof(float) + (2 * kMaxStages + 2) * 8; }
-  static constexpr size_t bytes(int stages) { return 1024 /*alignment slack*/ + (size_t)stages * kStageBytes + tail_bytes(); }
+  static constexpr int kBTileBytes = 2 * BN * kBK * 2;                 // B_hi + B_lo of one K step
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;         // two accumulator buffers
+  static constexpr size_t tail_bytes() {
+    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + (2 * kMaxStages + 8) * 8;
+  }
+  static constexpr size_t stage_bytes(bool resident) { return kAStageBytes + (resident ? 0 : kBTileBytes); }
+  static constexpr size_t bytes(int stages, bool resident, int k_iters) {
+    return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes(resident) + (resident ? (size_t)k_iters * kBTileBytes : 0) +
+           tail_bytes();
+  }
 };
 
+// Persistent, warp-specialised implicit-GEMM convolution.  Every CTA walks the output tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across tile boundaries through one shared-memory
+// ring, the MMA thread alternates between two TMEM accumulator buffers, and the eight epilogue warps drain buffer i
+// while the tensor pipe fills buffer i^1.
 template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using S = ConvSmem<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* stage_base = smem;
   const int n_stages = p.n_stages;
-  float* s_bias = reinterpret_cast<float*>(smem + (size_t)n_stages * S::kStageBytes);   // [2][BN]
-  float* s_head = s_bias + 2 * BN;                // [kMaxHeadOut][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_head + kMaxHeadOut * BN);
+  const int k_iters = p.ntaps * p.kblocks;
+  const bool resident = p.b_resident != 0;
+  const int stage_bytes = (int)S::stage_bytes(resident);
+  unsigned char* stage_base = smem;
+  unsigned char* bres = smem + (size_t)n_stages * stage_bytes;                     // resident weights (optional)
+  float* s_bias = reinterpret_cast<float*>(bres + (resident ? (size_t)k_iters * S::kBTileBytes : 0));   // [BN]
+  float* s_head = s_bias + BN;                    // [kMaxHeadOut][BN]
+  float* s_hx = s_head + kMaxHeadOut * BN;        // [kMaxHeadOut][128] head partials handed between column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hx + kMaxHeadOut * 128);
   uint64_t* full_bar = bars;                      // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;        // [kMaxStages]
-  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;  // [2]
+  uint64_t* bres_bar = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-  const int img = tile;
-  const int bidx = img / p.T, tidx = p.t0 + img % p.T;
-  const int ox0 = tx * kTileW, oy0 = ty * kTileH;
-  const int k_iters = p.ntaps * p.kblocks;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
     for (int i = 0; i < n_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
-  for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-    s_bias[i] = p.bias[i];
-    s_bias[BN + i] = p.img_bias ? p.img_bias[(size_t)img * BN + i] : 0.f;
-  }
+  for (int i = threadIdx.x; i < BN; i += blockDim.x) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < p.head_ko * BN; i += blockDim.x) s_head[i] = p.head_w[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (resident) {
+        ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
+        for (int it = 0; it < k_iters; ++it) {
+          ptx::tma_load_2d(bres + (size_t)it * S::kBTileBytes, &tm_w, bres_bar, 0, (it * 2) * BN);
+          ptx::tma_load_2d(bres + (size_t)it * S::kBTileBytes + BN * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * BN);
+        }
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        const int tap = it / p.kblocks, kb = it % p.kblocks;
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        unsigned char* sa_hi = stage_base + (size_t)stage * S::kStageBytes;
-        unsigned char* sa_lo = sa_hi + 128 * kBK * 2;
-        unsigned char* sb_hi = sa_lo + 128 * kBK * 2;
-        unsigned char* sb_lo = sb_hi + BN * kBK * 2;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-        const int c = p.cin_off + kb * kBK;
-        const int x = ox0 * p.stride + p.tap[tap][2];
-        const int y = oy0 * p.stride + p.tap[tap][1];
-        const int t = tidx + p.tap[tap][0];
-        ptx::tma_load_5d(sa_hi, &tm_a_hi, &full_bar[stage], c, x, y, t, bidx);
-        ptx::tma_load_5d(sa_lo, &tm_a_lo, &full_bar[stage], c, x, y, t, bidx);
-        const int wrow = (it * 2) * BN;            // [tap][kb][plane][BN] rows of 64
-        ptx::tma_load_2d(sb_hi, &tm_w, &full_bar[stage], 0, wrow);
-        ptx::tma_load_2d(sb_lo, &tm_w, &full_bar[stage], 0, wrow + BN);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+        const int oy0 = (rem / p.tiles_x) * kTileH, ox0 = (rem % p.tiles_x) * kTileW;
+        const int bidx = img / p.T, tidx = p.t0 + img % p.T;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.kblocks, kb = it % p.kblocks;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa_hi = stage_base + (size_t)stage * stage_bytes;
+          unsigned char* sa_lo = sa_hi + 128 * kBK * 2;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const int c = p.cin_off + kb * kBK;
+          const int x = ox0 * p.stride + p.tap[tap][2];
+          const int y = oy0 * p.stride + p.tap[tap][1];
+          const int t = tidx + p.tap[tap][0];
+          ptx::tma_load_5d(sa_hi, &tm_a_hi, &full_bar[stage], c, x, y, t, bidx);
+          ptx::tma_load_5d(sa_lo, &tm_a_lo, &full_bar[stage], c, x, y, t, bidx);
+          if (!resident) {
+            unsigned char* sb_hi = sa_lo + 128 * kBK * 2;
+            ptx::tma_load_2d(sb_hi, &tm_w, &full_bar[stage], 0, (it * 2) * BN);       // [tap][kb][plane][BN] rows of 64
+            ptx::tma_load_2d(sb_hi + BN * kBK * 2, &tm_w, &full_bar[stage], 0, (it * 2 + 1) * BN);
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      if (resident) ptx::mbar_wait(bres_bar, 0);
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+      int buf = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // the epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)stage * S::kStageBytes);
-        const uint32_t a_lo = a_hi + 128 * kBK * 2;
-        const uint32_t b_hi = a_lo + 128 * kBK * 2;
-        const uint32_t b_lo = b_hi + BN * kBK * 2;
-        const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_lo);
-        const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_lo);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int it = 0; it < k_iters; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)stage * stage_bytes);
+          const uint32_t a_lo = a_hi + 128 * kBK * 2;
+          const uint32_t b_hi = resident ? ptx::smem_u32(bres + (size_t)it * S::kBTileBytes) : a_lo + 128 * kBK * 2;
+          const uint32_t b_lo = b_hi + BN * kBK * 2;
+          const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_lo);
+          const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_lo);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
-          ptx::umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
-          ptx::umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1);
-          ptx::umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, 1);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
+            ptx::umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
+            ptx::umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+            ptx::umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+          }
+          ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
-        if (it == k_iters - 1) ptx::umma_commit(tmem_full_bar);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        ptx::umma_commit(&tmem_full_bar[buf]);          // accumulator complete -> epilogue
+        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int e = warp - 2;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = e >> 2;                     // which half of the BN columns this warp handles
+    constexpr int kColsPerWarp = BN / 2;
+    const int col0 = half * kColsPerWarp;
     const int r = q * 32 + lane;                 // row of the tile = output pixel
-    const int oy = oy0 + (r >> 4), ox = ox0 + (r & 15);
-    const bool valid = oy < p.Ho && ox < p.Wo;
-    const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
-    float hacc[kMaxHeadOut];
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+      const int oy = (rem / p.tiles_x) * kTileH + (r >> 4), ox = (rem % p.tiles_x) * kTileW + (r & 15);
+      const bool valid = oy < p.Ho && ox < p.Wo;
+      const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+      const float* ib = p.img_bias ? p.img_bias + (size_t)img * BN : nullptr;
+      float hacc[kMaxHeadOut];
 #pragma unroll
-    for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
+      for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
+      ptx::mbar_wait(&tmem_full_bar[buf], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0);
 #pragma unroll 1
-    for (int j = 0; j < BN / 16; ++j) {
-      uint32_t acc[16];
-      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + j * 16, acc);
-      ptx::tmem_ld_wait();
-      if (valid) {
-        float v[16];
+      for (int j = 0; j < kColsPerWarp / 16; ++j) {
+        const int cb = col0 + j * 16;              // first output channel of this chunk
+        uint32_t acc[16];
+        ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[j * 16 + i] + s_bias[BN + j * 16 + i];
-        if (p.res_mode) {
-          const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + j * 16);
-          const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + j * 16);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[cb + i];
+          if (ib) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(ib + cb + i);
+          }
+          if (p.res_mode) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + cb);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + cb);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float r0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-              const float r1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
-              float& a0 = v[g * 8 + e * 2], &a1 = v[g * 8 + e * 2 + 1];
-              if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
-              else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+            for (int g = 0; g < 2; ++g) {
+              const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float r0 = __uint_as_float(hw[e2] << 16) + __uint_as_float(lw[e2] << 16);
+                const float r1 = __uint_as_float(hw[e2] & 0xFFFF0000u) + __uint_as_float(lw[e2] & 0xFFFF0000u);
+                float& a0 = v[g * 8 + e2 * 2], &a1 = v[g * 8 + e2 * 2 + 1];
+                if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
+                else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+              }
+            }
+          } else if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.out_hi) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + cb);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + cb);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (cb + g * 8 >= p.n_store) break;
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float x0 = v[g * 8 + e2 * 2], x1 = v[g * 8 + e2 * 2 + 1];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hw[e2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
           }
-        } else if (p.relu) {
+          if (p.out_f32) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.out_hi) {
-          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + j * 16);
-          uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + j * 16);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (j * 16 + g * 8 >= p.n_store) break;
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-              hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            for (int i = 0; i < 16; ++i) {
+              const int c = cb + i;
+              if (c < p.n_valid) {
+                float x = v[i];
+                if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
+                p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
+              }
             }
-            oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
-        }
-        if (p.out_f32) {
+          if (p.head_ko) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = j * 16 + i;
-            if (c < p.n_valid) {
-              float x = v[i];
-              if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
-              p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
+            for (int k = 0; k < kMaxHeadOut; ++k) {
+              if (k < p.head_ko) {
+                const float* w = s_head + k * BN + cb;
+                float a = hacc[k];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a = fmaf(w[i], v[i], a);
+                hacc[k] = a;
+              }
             }
           }
         }
-        if (p.head_ko) {
+      }
+      // this warp has finished reading the accumulator buffer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+      if (p.head_ko) {
+        // the two column halves of a pixel live in two warps of the same lane quarter: the upper half hands its
+        // partial dot products over through shared memory (named barrier of the 64 threads involved)
+        if (half == 1) {
+#pragma unroll
+          for (int k = 0; k < kMaxHeadOut; ++k) if (k < p.head_ko) s_hx[k * 128 + r] = hacc[k];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        if (half == 0 && valid) {
 #pragma unroll
           for (int k = 0; k < kMaxHeadOut; ++k) {
             if (k < p.head_ko) {
-              const float* w = s_head + k * BN + j * 16;
-              float a = hacc[k];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) a = fmaf(w[i], v[i], a);
-              hacc[k] = a;
+              float x = hacc[k] + s_hx[k * 128 + r] + p.head_b[k];
+              if (p.head_sigmoid_mask & (1 << k)) x = 1.f / (1.f + __expf(-x));
+              p.head_out[k][(size_t)img * p.head_img_stride[k] + (size_t)oy * p.Wo + ox] = x;
             }
           }
         }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       }
-    }
-    if (p.head_ko && valid) {
-#pragma unroll
-      for (int k = 0; k < kMaxHeadOut; ++k) {
-        if (k < p.head_ko) {
-          float x = hacc[k] + p.head_b[k];
-          if (p.head_sigmoid_mask & (1 << k)) x = 1.f / (1.f + __expf(-x));
-          p.head_out[k][(size_t)img * p.head_img_stride[k] + (size_t)oy * p.Wo + ox] = x;
-        }
-      }
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   }
   ptx::tc_fence_before();
@@ -365,31 +429,32 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     p.head_ko = head->n_out; p.head_w = head->w; p.head_b = head->b; p.head_sigmoid_mask = head->sigmoid_mask;
     for (int k = 0; k < head->n_out; ++k) { p.head_out[k] = head->out[k]; p.head_img_stride[k] = head->img_stride[k]; }
   }
-  // smem ring depth: no deeper than the K loop, and shallow enough that two CTAs share an SM (their load, MMA and
-  // epilogue phases then overlap; a single-tile CTA has no other way to hide its epilogue)
   const int k_iters = d->ntaps * kblocks;
-
   const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;
   STP3_CHECK_ARG(nblk > 0 && nblk < (1ll << 31), "grid too large");
-  // policy 1 (default, measured fastest): always favour 2 CTAs/SM.  policy 0: BN=128 with a long K loop keeps
-  // a 3-deep ring on one CTA.  policy 2: one CTA/SM, deepest ring.  (STP3_CONV_POLICY, for A/B measurements.)
-  static const int policy = [] { const char* e = getenv("STP3_CONV_POLICY"); return e ? atoi(e) : 1; }();
+  p.n_tiles = (int)nblk;
+  static const int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const unsigned grid = (unsigned)(nblk < num_sms ? nblk : num_sms);     // persistent: one CTA per SM
+  const size_t smem_cap = 227 * 1024;
 #define STP3_LAUNCH_CONV(BN_)                                                                                     \
   do {                                                                                                            \
-    const int max_st = BN_ == 64 ? 4 : (BN_ == 128 ? 3 : 2);                                                      \
-    const int budget = 112 * 1024; /* per CTA, so that two fit in 227 KB */                                       \
-    int st = (int)((budget - 1024 - ConvSmem<BN_>::tail_bytes()) / ConvSmem<BN_>::kStageBytes);                   \
-    if (st < 1) st = 1;                                                                                           \
-    if (BN_ == 256) st = 2;        /* 96 KB stages: one CTA per SM, two stages */                                  \
-    if (BN_ == 128 && k_iters > 2 && policy == 0) st = 3;                                                         \
-    if (policy == 2) st = max_st;  /* one CTA per SM, deepest ring (the v1 behaviour) */                          \
-    if (st > k_iters) st = k_iters;                                                                               \
-    if (st > max_st) st = max_st;                                                                                 \
-    p.n_stages = st;                                                                                              \
-    const size_t smem_bytes = ConvSmem<BN_>::bytes(st);                                                           \
+    using SM = ConvSmem<BN_>;                                                                                     \
+    /* keep the whole weight tensor in smem when it leaves room for >= 3 activation stages */                     \
+    const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                      \
+    const bool res = 1024 + wbytes + 3 * SM::stage_bytes(true) + SM::tail_bytes() <= smem_cap;                    \
+    int st = (int)((smem_cap - 1024 - SM::tail_bytes() - (res ? wbytes : 0)) / SM::stage_bytes(res));             \
+    if (st > kMaxStages) st = kMaxStages;                                                                         \
+    if (st < 2) return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");                 \
+    p.n_stages = st; p.b_resident = res ? 1 : 0;                                                                  \
+    const size_t smem_bytes = SM::bytes(st, res, k_iters);                                                        \
     STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      (int)ConvSmem<BN_>::bytes(max_st)));                                        \
-    conv_igemm_kernel<BN_><<<(unsigned)nblk, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);          \
+                                      (int)smem_cap));                                                            \
+    conv_igemm_kernel<BN_><<<grid, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);                     \
   } while (0)
   if (d->bn == 64) STP3_LAUNCH_CONV(64);
   else if (d->bn == 128) STP3_LAUNCH_CONV(128);
