@@ -98,7 +98,8 @@ int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_l
  * tensor pipe reproduces fp32 convolution to ~1e-5 (three MMAs per product: hi*hi + hi*lo + lo*hi):
  *   x_hi, x_lo   (B, T, H, W, in_cstride) bf16, in_cstride % 64 == 0, padding channels zero
  *   w            [ntaps][cin/64][2 planes][bn][64] bf16: tap-major, K-major rows of 64 input channels
- *   bias         [bn] fp32;  img_bias  optional [B*T][bn] fp32
+ *   bias         [bn] fp32;  img_bias  optional [B*T][bn] fp32: per-image bias table that REPLACES bias (it must
+ *                already contain it): the spatially constant branches and the ego-motion channels enter here
  *   res_hi/lo    optional residual (B*T, Ho, Wo, res_cstride), channels [res_coff, res_coff+bn)
  *   y_hi, y_lo   optional output planes (B*T, Ho, Wo, out_cstride), channels [out_coff, out_coff+bn)
  *   y_f32        optional (B*T, n_valid, Ho, Wo) fp32 in the reference's NCHW layout (final logits)

@@ -94,7 +94,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using S = ConvSmem<BN>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128-byte swizzle; plain offset arithmetic keeps the pointer in the shared state space
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int n_stages = p.n_stages;
   const int k_iters = p.ntaps * p.kblocks;
   const bool resident = p.b_resident != 0;
@@ -230,10 +231,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         if (valid) {
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + s_bias[cb + i];
-          if (ib) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(ib + cb + i);
+          for (int g = 0; g < 4; ++g) {          // bias: per-image table (conv bias already folded in) or smem
+            const float4 b4 = ib ? __ldg(reinterpret_cast<const float4*>(ib + cb) + g)
+                                 : *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
+            v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
+            v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
+            v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
+            v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
           }
           if (p.res_mode) {
             const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + cb);
@@ -265,11 +269,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
                 const float x0 = v[g * 8 + e2 * 2], x1 = v[g * 8 + e2 * 2 + 1];
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                hw[e2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[e2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                const uint32_t h = ptx::pack_bf16x2(x0, x1);                 // one cvt.rn.bf16x2.f32
+                const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
+                hw[e2] = h;
+                lw[e2] = ptx::pack_bf16x2(r0, r1);
               }
               oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
               ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);

@@ -449,27 +449,42 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
   }
 }
 
-// pool_sum[b,t,c] = sum over the finalize CTAs' partials (B, nblk, S, C); grid (B*S), block (32, 8)
-// (the partials are zeroed again after they are read: the whole workspace stays all-zero between calls)
+// pool_sum[b,t,c] += sum over a slice of the finalize CTAs' partials (B, nblk, S, C); grid (B*S, kPoolSlices),
+// block (32, 8).  All loads of a thread are issued before the partials are zeroed again (the whole workspace stays
+// all-zero between calls); pool_sum is cleared by the caller (cudaMemsetAsync in stp3_lift_splat_fwd).
+constexpr int kPoolSlices = 16;
 __global__ void pool_reduce_kernel(float* __restrict__ part, int nblk, int S, int C, float* __restrict__ out) {
   __shared__ float sm[8][33];
   const int b = blockIdx.x / S, t = blockIdx.x % S;
+  const int per = (nblk + kPoolSlices - 1) / kPoolSlices;
+  const int k0 = blockIdx.y * per, k1 = min(nblk, k0 + per);
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + threadIdx.x;
     float a = 0.f;
-    if (c < C)
-      for (int k = threadIdx.y; k < nblk; k += 8) {
-        float* src = part + (((size_t)b * nblk + k) * S + t) * C + c;
-        a += *src;
-        *src = 0.f;
+    if (c < C) {
+      constexpr int kMaxLoads = 16;
+      for (int kb = k0 + threadIdx.y; kb < k1; kb += 8 * kMaxLoads) {
+        float v[kMaxLoads];
+#pragma unroll
+        for (int i = 0; i < kMaxLoads; ++i) {
+          const int k = kb + 8 * i;
+          v[i] = k < k1 ? part[(((size_t)b * nblk + k) * S + t) * C + c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxLoads; ++i) {
+          const int k = kb + 8 * i;
+          a += v[i];
+          if (k < k1) part[(((size_t)b * nblk + k) * S + t) * C + c] = 0.f;
+        }
       }
+    }
     sm[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
       float tot = 0.f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) tot += sm[r][threadIdx.x];
-      out[(size_t)blockIdx.x * C + c] = tot;
+      atomicAdd(out + (size_t)blockIdx.x * C + c, tot);
     }
     __syncthreads();
   }
@@ -583,7 +598,8 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
 #undef STP3_FINALIZE
   STP3_CUDA_OK(cudaGetLastError());
   if (pool_sum) {
-    pool_reduce_kernel<<<B * S, dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), S, C, pool_sum);
+    STP3_CUDA_OK(cudaMemsetAsync(pool_sum, 0, (size_t)B * S * C * sizeof(float), stream));
+    pool_reduce_kernel<<<dim3(B * S, kPoolSlices), dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), S, C, pool_sum);
     STP3_CUDA_OK(cudaGetLastError());
   }
   if (groups > 1) {

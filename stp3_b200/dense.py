@@ -129,7 +129,8 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
          out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
          head: Optional[dict] = None, store: bool = True) -> Optional[HL]:
-    """y = act(conv(x[..., cin_off:cin_off+cin]) + bias + img_bias [+ residual]) written into out[..., out_coff:...]."""
+    """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
+    img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table())."""
     B, T_total, H, W, cs = x.hi.shape
     t0, T = frames if frames is not None else (0, T_total)      # process frames [t0, t0+T) of every sample
     Ho, Wo = out_hw if out_hw is not None else ((H + pc.stride - 1) // pc.stride, (W + pc.stride - 1) // pc.stride)
@@ -177,6 +178,12 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
             ctypes.byref(hd) if hd is not None else None, torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(code, "stp3_conv_fwd")
     return out
+
+
+def bias_table(pc: PackedConv, n_img: int) -> torch.Tensor:
+    """(n_img, bn) per-image bias initialised with the convolution's own bias; the spatially constant branches are
+    accumulated on top (pool_bias / small_linear with accumulate=True)."""
+    return pc.bias.unsqueeze(0).expand(n_img, -1).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------ aux kernels

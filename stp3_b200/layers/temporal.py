@@ -150,20 +150,20 @@ class TemporalBlock(PackedModule):
         cin, half, cout, o, cs = self.in_channels, self.half_channels, self.out_channels, P["o"], P["cs"]
         n_img = B * T
 
-        def const_bias(wc, bn):
+        def const_bias(wc, pc):
             if not nc:
                 return None
-            b = torch.empty((n_img, bn), dtype=torch.float32, device=dev)
-            dense.small_linear(const, wc, b, False)
+            b = dense.bias_table(pc, n_img)
+            dense.small_linear(const, wc, b, True)
             return b
 
-        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), 128))
+        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
         agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=128)
         if 3 * o < 128:
             agg.hi[..., 3 * o:].zero_(); agg.lo[..., 3 * o:].zero_()      # padding channels of the concat tensor
         dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
         dense.conv(mid, P["c"], cin_off=64, out=agg, out_coff=o, n_store=o, relu=True)
-        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=o, relu=True, img_bias=const_bias(P.get("a2_c"), 64))
+        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=o, relu=True, img_bias=const_bias(P.get("a2_c"), P["a2"]))
         pbias = None
         if self.use_pyramid_pooling:
             ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
@@ -174,10 +174,10 @@ class TemporalBlock(PackedModule):
             full[:, :cs] = sums[:, :cs]
             if nc:
                 full[:, cs:] = const * float(H * W)
-            pbias = torch.empty((n_img, P["agg"].bn), dtype=torch.float32, device=dev)
-            dense.pool_bias(full, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False)
+            pbias = dense.bias_table(P["agg"], n_img)
+            dense.pool_bias(full, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, True)
         if self.projection is not None:
-            res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"].bn))
+            res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"]))
         else:
             assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
             res = x

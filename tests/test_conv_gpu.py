@@ -95,6 +95,7 @@ def test_epilogue_fusions():
     ib = rnd(B * T, 64, seed=11)
     pc = dense.pack_conv(w.to(DEV), b.to(DEV))
     base = ref_conv2d(x, w, b) + ib.view(B, T, 64, 1, 1).double()
+    ib = ib + b.view(1, 64)          # the per-image table replaces the bias vector, so it carries it
     # residual before the activation (ResNet BasicBlock), written at a channel offset of a wider tensor
     out = dense.HL.zeros(B, T, H, W, 192, DEV)
     dense.conv(to_hl(x), pc, out=out, out_coff=64, relu=True, img_bias=ib.to(DEV), residual=to_hl(res))
