@@ -11,13 +11,14 @@
 // folded into the weights/bias on the host; bias, per-image bias (pyramid-pool / ASPP-pool / ego-motion
 // branches), ReLU, residual add and the concat offset are fused in the epilogue.
 //
-//   tile     : 128 output pixels (8 rows x 16 columns of one image) x BN output channels (64 / 128 / 256)
-//   K loop   : taps x (Cin / 64); per step TMA brings A_hi, A_lo (128x64 bf16, 128B-swizzled) and B_hi, B_lo
-//              (BN x 64; small weight tensors stay resident in smem) and one thread issues 4 (UMMA_K=16) x 3
-//              tcgen05.mma into one of TWO TMEM accumulator buffers
-//   CTA      : persistent, one per SM, walks tiles blockIdx.x + i*gridDim.x through one smem ring
+//   tile     : 256 output pixels (16 x 16 of one image = two UMMA M=128 sub-tiles sharing every weight tile) x BN
+//              output channels (64 / 128; 256 runs as two launches)
+//   K loop   : taps x (Cin / 64); TMA brings A_hi, A_lo (256 or 288 pixel rows x 64 bf16, 128B-swizzled; one load
+//              serves the three dy taps of a 3x3) and B_hi, B_lo (BN x 64; small weight tensors stay resident in
+//              smem) through separate rings; one thread issues 2 x 4 (UMMA_K=16) x 3 tcgen05.mma per tap
+//   CTA      : persistent, one per SM, walks tiles blockIdx.x + i*gridDim.x
 //   warps    : 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (TMEM -> regs -> global), which
-//              drains accumulator i while the tensor pipe fills accumulator i^1
+//              drains one accumulator pair while the tensor pipe fills the other
 //
 // Reference layers: stp3/layers/temporal.py:252-489, stp3/layers/convolutions.py:183-280, stp3/models/decoder.py.
 #include <cuda_bf16.h>
@@ -31,12 +32,11 @@ namespace stp3 {
 
 constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int kConvThreads = 64 + kEpiWarps * 32;
-constexpr int kTileH = 8, kTileW = 16;          // 128 output pixels = UMMA M
+constexpr int kTileH = 16, kTileW = 16;         // 256 output pixels = two UMMA M=128 sub-tiles (rows 0-7 and 8-15)
 constexpr int kBK = 64;                         // channels per K step (one 128-byte swizzle row of bf16)
 constexpr int kMaxTaps = 49;
-constexpr int kMaxStages = 8;
+constexpr int kMaxAStages = 4, kMaxBStages = 8;
 constexpr int kMaxHeadOut = 8;
-constexpr int kAStageBytes = 2 * 128 * kBK * 2; // A_hi + A_lo tiles of one K step
 
 struct ConvParams {
   int n_img, T, t0, Ho, Wo;
@@ -45,9 +45,14 @@ struct ConvParams {
   int kblocks;              // Cin / 64 of this convolution
   int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
   int ntaps;
+  int group;                // taps that share one activation load: 3 = the three dy taps of a 3x3 (stride 1, dilation 1)
+  int a_plane_bytes;        // bytes of one activation plane of a stage = box_h * 16 px * 128 B
+  int w_rows;               // rows per (tap, kb, plane) block of the packed weight tensor (the convolution's padded Cout)
+  int w_row_off;            // first row of this launch inside that block (a 256-channel conv runs as two launches)
   signed char tap[kMaxTaps][4];   // (dt, dy, dx): input coordinate = output coordinate * stride + d
   const float* bias;        // [BN]
-  const float* img_bias;    // [n_img][BN] or null
+  const float* img_bias;    // [n_img][img_bias_stride] or null (replaces bias)
+  int img_bias_stride;
   int relu;
   int res_mode;             // 0 none, 1 residual added before the activation, 2 after
   const __nv_bfloat16* res_hi;
@@ -57,9 +62,9 @@ struct ConvParams {
   __nv_bfloat16* out_lo;
   int out_cstride, out_coff, n_store;
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
-  int n_valid;
+  int n_valid, f32_coff;    // channel offset of this launch inside out_f32
   int sigmoid;              // apply to out_f32 (instance_center head)
-  int n_stages;             // smem ring depth chosen by the host (2 .. kMaxStages)
+  int na_stages, nb_stages; // smem ring depths chosen by the host
   int b_resident;           // all weight tiles of the convolution stay in shared memory for the CTA's lifetime
   // fused 1x1 "head" on the activated tile: out_k = head_b[k] + sum_c head_w[k][c] * y[c]  (decoder heads 3x3 -> 1x1)
   int head_ko;              // 0 = off, else 1..8 outputs
@@ -73,21 +78,21 @@ struct ConvParams {
 template <int BN>
 struct ConvSmem {
   static constexpr int kBTileBytes = 2 * BN * kBK * 2;                 // B_hi + B_lo of one K step
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;         // two accumulator buffers
+  static constexpr int kTmemCols = 4 * BN;                             // 2 sub-tiles x 2 accumulator buffers
   static constexpr size_t tail_bytes() {
-    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + (2 * kMaxStages + 8) * 8;
-  }
-  static constexpr size_t stage_bytes(bool resident) { return kAStageBytes + (resident ? 0 : kBTileBytes); }
-  static constexpr size_t bytes(int stages, bool resident, int k_iters) {
-    return 1024 /*alignment slack*/ + (size_t)stages * stage_bytes(resident) + (resident ? (size_t)k_iters * kBTileBytes : 0) +
-           tail_bytes();
+    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) +
+           (2 * kMaxAStages + 2 * kMaxBStages + 8) * 8;
   }
 };
 
-// Persistent, warp-specialised implicit-GEMM convolution.  Every CTA walks the output tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across tile boundaries through one shared-memory
-// ring, the MMA thread alternates between two TMEM accumulator buffers, and the eight epilogue warps drain buffer i
-// while the tensor pipe fills buffer i^1.
+// Persistent, warp-specialised implicit-GEMM convolution.
+//   * A CTA walks output tiles blockIdx.x + i*gridDim.x; a tile is 16x16 pixels = two M=128 sub-tiles that share every
+//     weight tile (B traffic per flop halves).
+//   * Activations and weights travel through separate shared-memory rings.  For 3x3 / stride 1 / dilation 1 kernels one
+//     activation load of 18 image rows serves the three dy taps: their A operands are the same smem tile at row
+//     offsets 0, 16, 32 (2 KB steps keep the 1024-byte swizzle alignment), so A traffic drops 2.4x.
+//   * The MMA thread alternates between two TMEM accumulator buffers; eight epilogue warps drain one while the tensor
+//     pipe fills the other.
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -96,28 +101,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain offset arithmetic keeps the pointer in the shared state space
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int n_stages = p.n_stages;
   const int k_iters = p.ntaps * p.kblocks;
   const bool resident = p.b_resident != 0;
-  const int stage_bytes = (int)S::stage_bytes(resident);
-  unsigned char* stage_base = smem;
-  unsigned char* bres = smem + (size_t)n_stages * stage_bytes;                     // resident weights (optional)
-  float* s_bias = reinterpret_cast<float*>(bres + (resident ? (size_t)k_iters * S::kBTileBytes : 0));   // [BN]
+  const int a_stage_bytes = 2 * p.a_plane_bytes;
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = a_ring + (size_t)p.na_stages * a_stage_bytes;            // ring, or the resident weights
+  float* s_bias = reinterpret_cast<float*>(b_ring + (size_t)(resident ? k_iters : p.nb_stages) * S::kBTileBytes);
   float* s_head = s_bias + BN;                    // [kMaxHeadOut][BN]
   float* s_hx = s_head + kMaxHeadOut * BN;        // [kMaxHeadOut][128] head partials handed between column halves
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_hx + kMaxHeadOut * 128);
-  uint64_t* full_bar = bars;                      // [kMaxStages]
-  uint64_t* empty_bar = bars + kMaxStages;        // [kMaxStages]
-  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;       // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;  // [2]
-  uint64_t* bres_bar = bars + 2 * kMaxStages + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxAStages;
+  uint64_t* b_full = a_empty + kMaxAStages;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* tmem_full_bar = b_empty + kMaxBStages;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint64_t* bres_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
-    for (int i = 0; i < n_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < p.na_stages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.nb_stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_mbar_init();
@@ -130,6 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_groups = p.ntaps / p.group;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -137,33 +145,41 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       if (resident) {
         ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
         for (int it = 0; it < k_iters; ++it) {
-          ptx::tma_load_2d(bres + (size_t)it * S::kBTileBytes, &tm_w, bres_bar, 0, (it * 2) * BN);
-          ptx::tma_load_2d(bres + (size_t)it * S::kBTileBytes + BN * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * BN);
+          unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
+          ptx::tma_load_2d(dst, &tm_w, bres_bar, 0, (it * 2) * p.w_rows + p.w_row_off);
+          ptx::tma_load_2d(dst + BN * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
         }
       }
-      int stage = 0; uint32_t phase = 0;
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
         const int oy0 = (rem / p.tiles_x) * kTileH, ox0 = (rem % p.tiles_x) * kTileW;
         const int bidx = img / p.T, tidx = p.t0 + img % p.T;
-        for (int it = 0; it < k_iters; ++it) {
-          const int tap = it / p.kblocks, kb = it % p.kblocks;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa_hi = stage_base + (size_t)stage * stage_bytes;
-          unsigned char* sa_lo = sa_hi + 128 * kBK * 2;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          const int c = p.cin_off + kb * kBK;
-          const int x = ox0 * p.stride + p.tap[tap][2];
-          const int y = oy0 * p.stride + p.tap[tap][1];
-          const int t = tidx + p.tap[tap][0];
-          ptx::tma_load_5d(sa_hi, &tm_a_hi, &full_bar[stage], c, x, y, t, bidx);
-          ptx::tma_load_5d(sa_lo, &tm_a_lo, &full_bar[stage], c, x, y, t, bidx);
-          if (!resident) {
-            unsigned char* sb_hi = sa_lo + 128 * kBK * 2;
-            ptx::tma_load_2d(sb_hi, &tm_w, &full_bar[stage], 0, (it * 2) * BN);       // [tap][kb][plane][BN] rows of 64
-            ptx::tma_load_2d(sb_hi + BN * kBK * 2, &tm_w, &full_bar[stage], 0, (it * 2 + 1) * BN);
+        for (int grp = 0; grp < n_groups; ++grp) {
+          const int tap0 = grp * p.group;
+          const int x = ox0 * p.stride + p.tap[tap0][2];
+          const int y = oy0 * p.stride + p.tap[tap0][1];
+          const int t = tidx + p.tap[tap0][0];
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&a_empty[as], aph ^ 1);
+            unsigned char* sa = a_ring + (size_t)as * a_stage_bytes;
+            ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
+            const int c = p.cin_off + kb * kBK;
+            ptx::tma_load_5d(sa, &tm_a_hi, &a_full[as], c, x, y, t, bidx);
+            ptx::tma_load_5d(sa + p.a_plane_bytes, &tm_a_lo, &a_full[as], c, x, y, t, bidx);
+            if (++as == p.na_stages) { as = 0; aph ^= 1; }
+            if (!resident) {
+              for (int j = 0; j < p.group; ++j) {
+                const int it = (tap0 + j) * p.kblocks + kb;          // [tap][kb][plane][rows] blocks of 64-wide rows
+                ptx::mbar_wait(&b_empty[bs], bph ^ 1);
+                unsigned char* sb = b_ring + (size_t)bs * S::kBTileBytes;
+                ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
+                ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + p.w_row_off);
+                ptx::tma_load_2d(sb + BN * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
+                if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
+              }
+            }
           }
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -172,32 +188,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
       if (resident) ptx::mbar_wait(bres_bar, 0);
-      int stage = 0; uint32_t phase = 0;
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       int buf = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // the epilogue has drained this accumulator
+        ptx::mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // the epilogue has drained this accumulator pair
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        for (int it = 0; it < k_iters; ++it) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)stage * stage_bytes);
-          const uint32_t a_lo = a_hi + 128 * kBK * 2;
-          const uint32_t b_hi = resident ? ptx::smem_u32(bres + (size_t)it * S::kBTileBytes) : a_lo + 128 * kBK * 2;
-          const uint32_t b_lo = b_hi + BN * kBK * 2;
-          const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_lo);
-          const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_lo);
+        uint32_t accumulate = 0;
+        for (int grp = 0; grp < n_groups; ++grp) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&a_full[as], aph);
+            ptx::tc_fence_after();
+            const uint32_t a_hi0 = ptx::smem_u32(a_ring + (size_t)as * a_stage_bytes);
+            for (int j = 0; j < p.group; ++j) {
+              const int it = (grp * p.group + j) * p.kblocks + kb;
+              uint32_t b_hi;
+              if (resident) {
+                b_hi = ptx::smem_u32(b_ring + (size_t)it * S::kBTileBytes);
+              } else {
+                ptx::mbar_wait(&b_full[bs], bph);
+                ptx::tc_fence_after();
+                b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
+              }
+              const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + BN * kBK * 2);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
-            ptx::umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (it | k) != 0);
-            ptx::umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-            ptx::umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+              for (int sub = 0; sub < 2; ++sub) {
+                // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
+                const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
+                const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_hi + p.a_plane_bytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + sub) * BN);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
+                  ptx::umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
+                  ptx::umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                  ptx::umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                }
+              }
+              accumulate = 1;
+              if (!resident) {
+                ptx::umma_commit(&b_empty[bs]);      // frees the weight slot when these MMAs have read it
+                if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
+              }
+            }
+            ptx::umma_commit(&a_empty[as]);          // frees the activation slot
+            if (++as == p.na_stages) { as = 0; aph ^= 1; }
           }
-          ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs have read it
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full_bar[buf]);          // accumulator complete -> epilogue
+        ptx::umma_commit(&tmem_full_bar[buf]);       // accumulators complete -> epilogue
         if (++buf == 2) { buf = 0; acc_phase ^= 1; }
       }
     }
@@ -208,125 +245,129 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int half = e >> 2;                     // which half of the BN columns this warp handles
     constexpr int kColsPerWarp = BN / 2;
     const int col0 = half * kColsPerWarp;
-    const int r = q * 32 + lane;                 // row of the tile = output pixel
+    const int r = q * 32 + lane;                 // row of the sub-tile = output pixel
     int buf = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int oy = (rem / p.tiles_x) * kTileH + (r >> 4), ox = (rem % p.tiles_x) * kTileW + (r & 15);
-      const bool valid = oy < p.Ho && ox < p.Wo;
-      const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
-      const float* ib = p.img_bias ? p.img_bias + (size_t)img * BN : nullptr;
-      float hacc[kMaxHeadOut];
-#pragma unroll
-      for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
+      const int oy_t = (rem / p.tiles_x) * kTileH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
+      const float* ib = p.img_bias ? p.img_bias + (size_t)img * p.img_bias_stride : nullptr;
       ptx::mbar_wait(&tmem_full_bar[buf], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0);
 #pragma unroll 1
-      for (int j = 0; j < kColsPerWarp / 16; ++j) {
-        const int cb = col0 + j * 16;              // first output channel of this chunk
-        uint32_t acc[16];
-        ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float v[16];
+      for (int sub = 0; sub < 2; ++sub) {
+        const int oy = oy_t + sub * 8 + (r >> 4);
+        const bool valid = oy < p.Ho && ox < p.Wo;
+        const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+        float hacc[kMaxHeadOut];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {          // bias: per-image table (conv bias already folded in) or smem
-            const float4 b4 = ib ? __ldg(reinterpret_cast<const float4*>(ib + cb) + g)
-                                 : *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
-            v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
-            v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
-            v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
-            v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
-          }
-          if (p.res_mode) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + cb);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + cb);
+        for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * BN + col0);
+#pragma unroll 1
+        for (int j = 0; j < kColsPerWarp / 16; ++j) {
+          const int cb = col0 + j * 16;              // first output channel of this chunk
+          uint32_t acc[16];
+          ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float v[16];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            for (int g = 0; g < 4; ++g) {          // bias: per-image table (conv bias already folded in) or smem
+              const float4 b4 = ib ? __ldg(reinterpret_cast<const float4*>(ib + cb) + g)
+                                   : *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
+              v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
+              v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
+              v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
+              v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
+            }
+            if (p.res_mode) {
+              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + cb);
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + cb);
 #pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                const float r0 = __uint_as_float(hw[e2] << 16) + __uint_as_float(lw[e2] << 16);
-                const float r1 = __uint_as_float(hw[e2] & 0xFFFF0000u) + __uint_as_float(lw[e2] & 0xFFFF0000u);
-                float& a0 = v[g * 8 + e2 * 2], &a1 = v[g * 8 + e2 * 2 + 1];
-                if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
-                else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+              for (int g = 0; g < 2; ++g) {
+                const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float r0 = __uint_as_float(hw[e2] << 16) + __uint_as_float(lw[e2] << 16);
+                  const float r1 = __uint_as_float(hw[e2] & 0xFFFF0000u) + __uint_as_float(lw[e2] & 0xFFFF0000u);
+                  float& a0 = v[g * 8 + e2 * 2], &a1 = v[g * 8 + e2 * 2 + 1];
+                  if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
+                  else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+                }
+              }
+            } else if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (p.out_hi) {
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + cb);
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + cb);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                if (cb + g * 8 >= p.n_store) break;
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const float x0 = v[g * 8 + e2 * 2], x1 = v[g * 8 + e2 * 2 + 1];
+                  const uint32_t h = ptx::pack_bf16x2(x0, x1);                 // one cvt.rn.bf16x2.f32
+                  const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
+                  hw[e2] = h;
+                  lw[e2] = ptx::pack_bf16x2(r0, r1);
+                }
+                oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }
             }
-          } else if (p.relu) {
+            if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.out_hi) {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + cb);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + cb);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (cb + g * 8 >= p.n_store) break;
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                const float x0 = v[g * 8 + e2 * 2], x1 = v[g * 8 + e2 * 2 + 1];
-                const uint32_t h = ptx::pack_bf16x2(x0, x1);                 // one cvt.rn.bf16x2.f32
-                const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
-                hw[e2] = h;
-                lw[e2] = ptx::pack_bf16x2(r0, r1);
+              for (int i = 0; i < 16; ++i) {
+                const int c = p.f32_coff + cb + i;
+                if (c < p.n_valid) {
+                  float x = v[i];
+                  if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
+                  p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
+                }
               }
-              oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
-          }
-          if (p.out_f32) {
+            if (p.head_ko) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = cb + i;
-              if (c < p.n_valid) {
-                float x = v[i];
-                if (p.sigmoid) x = 1.f / (1.f + __expf(-x));
-                p.out_f32[(((size_t)img * p.n_valid + c) * p.Ho + oy) * p.Wo + ox] = x;
+              for (int k = 0; k < kMaxHeadOut; ++k) {
+                if (k < p.head_ko) {
+                  const float* w = s_head + k * BN + cb;
+                  float a = hacc[k];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) a = fmaf(w[i], v[i], a);
+                  hacc[k] = a;
+                }
               }
             }
           }
-          if (p.head_ko) {
+        }
+        if (p.head_ko) {
+          // the two column halves of a pixel live in two warps of the same lane quarter: the upper half hands its
+          // partial dot products over through shared memory (named barrier of the 64 threads involved)
+          if (half == 1) {
+#pragma unroll
+            for (int k = 0; k < kMaxHeadOut; ++k) if (k < p.head_ko) s_hx[k * 128 + r] = hacc[k];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (half == 0 && valid) {
 #pragma unroll
             for (int k = 0; k < kMaxHeadOut; ++k) {
               if (k < p.head_ko) {
-                const float* w = s_head + k * BN + cb;
-                float a = hacc[k];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a = fmaf(w[i], v[i], a);
-                hacc[k] = a;
+                float x = hacc[k] + s_hx[k * 128 + r] + p.head_b[k];
+                if (p.head_sigmoid_mask & (1 << k)) x = 1.f / (1.f + __expf(-x));
+                p.head_out[k][(size_t)img * p.head_img_stride[k] + (size_t)oy * p.Wo + ox] = x;
               }
             }
           }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         }
       }
-      // this warp has finished reading the accumulator buffer
+      // this warp has finished reading the accumulator pair
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
-      if (p.head_ko) {
-        // the two column halves of a pixel live in two warps of the same lane quarter: the upper half hands its
-        // partial dot products over through shared memory (named barrier of the 64 threads involved)
-        if (half == 1) {
-#pragma unroll
-          for (int k = 0; k < kMaxHeadOut; ++k) if (k < p.head_ko) s_hx[k * 128 + r] = hacc[k];
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        if (half == 0 && valid) {
-#pragma unroll
-          for (int k = 0; k < kMaxHeadOut; ++k) {
-            if (k < p.head_ko) {
-              float x = hacc[k] + s_hx[k * 128 + r] + p.head_b[k];
-              if (p.head_sigmoid_mask & (1 << k)) x = 1.f / (1.f + __expf(-x));
-              p.head_out[k][(size_t)img * p.head_img_stride[k] + (size_t)oy * p.Wo + ox] = x;
-            }
-          }
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      }
       if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   }
@@ -364,6 +405,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   STP3_CHECK_ARG((y_hi && y_lo) || y_f32 || head, "stp3_conv_fwd: no output tensor");
   if (head) {
     STP3_CHECK_ARG(head->n_out >= 1 && head->n_out <= kMaxHeadOut && head->w && head->b, "bad fused head");
+    STP3_CHECK_ARG(d->bn <= 128, "a fused head needs bn <= 128");
     for (int k = 0; k < head->n_out; ++k) STP3_CHECK_ARG(head->out[k] != nullptr, "fused head: null output plane");
   }
   STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "non-positive dimension");
@@ -384,6 +426,18 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   PFN_tmapEncodeTiled enc = encode_fn();
   if (!enc) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
 
+  // taps that can share one activation load: consecutive triples (same dt, dx; dy, dy+1, dy+2) of a stride-1 kernel
+  int group = 1;
+  if (d->stride == 1 && d->ntaps % 3 == 0) {
+    group = 3;
+    for (int i = 0; i < d->ntaps && group == 3; i += 3)
+      for (int j = 1; j < 3; ++j)
+        if (d->taps[i + j][0] != d->taps[i][0] || d->taps[i + j][2] != d->taps[i][2] ||
+            d->taps[i + j][1] != d->taps[i][1] + j)
+          group = 1;
+  }
+  const int box_h = kTileH + (group - 1);
+
   CUtensorMap tm_hi, tm_lo, tm_w;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)d->in_cstride, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)T_total,
@@ -392,7 +446,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
                                    (cuuint64_t)d->H * d->W * d->in_cstride * 2,
                                    (cuuint64_t)T_total * d->H * d->W * d->in_cstride * 2};
     const cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)((kTileW - 1) * d->stride + 1),
-                               (cuuint32_t)((kTileH - 1) * d->stride + 1), 1, 1};
+                               (cuuint32_t)((box_h - 1) * d->stride + 1), 1, 1};
     const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
     CUresult r1 = enc(&tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_hi), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -404,10 +458,11 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d %d", (int)r1, (int)r2);
   }
   const int kblocks = d->cin / kBK;
+  const int bn_launch = d->bn == 256 ? 128 : d->bn;     // 256 output channels run as two 128-column launches
   {
     const cuuint64_t dims[2] = {(cuuint64_t)kBK, (cuuint64_t)d->ntaps * kblocks * 2 * d->bn};
     const cuuint64_t strides[1] = {(cuuint64_t)kBK * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)d->bn};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn_launch};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -419,13 +474,15 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, kTileH);
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
+  p.group = group; p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
-  p.bias = bias; p.img_bias = img_bias; p.relu = d->relu; p.res_mode = d->res_mode;
+  p.relu = d->relu; p.res_mode = d->res_mode;
   p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
-  p.res_cstride = d->res_cstride; p.res_coff = d->res_coff;
+  p.res_cstride = d->res_cstride;
   p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
-  p.out_cstride = d->out_cstride; p.out_coff = d->out_coff; p.n_store = n_store;
+  p.out_cstride = d->out_cstride;
   p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
+  p.img_bias_stride = d->bn;
   p.head_ko = 0; p.head_w = nullptr; p.head_b = nullptr; p.head_sigmoid_mask = 0;
   for (int k = 0; k < kMaxHeadOut; ++k) { p.head_out[k] = nullptr; p.head_img_stride[k] = 0; }
   if (head) {
@@ -444,25 +501,43 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   }();
   const unsigned grid = (unsigned)(nblk < num_sms ? nblk : num_sms);     // persistent: one CTA per SM
   const size_t smem_cap = 227 * 1024;
+  const size_t a_stage = 2 * (size_t)p.a_plane_bytes;
+
+  for (int part = 0; part * bn_launch < d->bn; ++part) {
+    const int coff = part * bn_launch;
+    p.w_row_off = coff;
+    p.bias = bias + coff;
+    p.img_bias = img_bias ? img_bias + coff : nullptr;
+    p.res_coff = d->res_coff + coff;
+    p.out_coff = d->out_coff + coff;
+    p.n_store = n_store - coff < bn_launch ? (n_store - coff > 0 ? n_store - coff : 0) : bn_launch;
+    p.f32_coff = coff;
 #define STP3_LAUNCH_CONV(BN_)                                                                                     \
-  do {                                                                                                            \
-    using SM = ConvSmem<BN_>;                                                                                     \
-    /* keep the whole weight tensor in smem when it leaves room for >= 3 activation stages */                     \
-    const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                      \
-    const bool res = 1024 + wbytes + 3 * SM::stage_bytes(true) + SM::tail_bytes() <= smem_cap;                    \
-    int st = (int)((smem_cap - 1024 - SM::tail_bytes() - (res ? wbytes : 0)) / SM::stage_bytes(res));             \
-    if (st > kMaxStages) st = kMaxStages;                                                                         \
-    if (st < 2) return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");                 \
-    p.n_stages = st; p.b_resident = res ? 1 : 0;                                                                  \
-    const size_t smem_bytes = SM::bytes(st, res, k_iters);                                                        \
-    STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      (int)smem_cap));                                                            \
-    conv_igemm_kernel<BN_><<<grid, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);                     \
-  } while (0)
-  if (d->bn == 64) STP3_LAUNCH_CONV(64);
-  else if (d->bn == 128) STP3_LAUNCH_CONV(128);
-  else STP3_LAUNCH_CONV(256);
+    do {                                                                                                          \
+      using SM = ConvSmem<BN_>;                                                                                   \
+      const size_t avail = smem_cap - 1024 - SM::tail_bytes();                                                    \
+      const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                    \
+      /* small weight tensors stay resident in smem next to >= 2 activation stages */                            \
+      const bool res = wbytes + 2 * a_stage <= avail;                                                             \
+      int na, nb;                                                                                                 \
+      if (res) {                                                                                                  \
+        na = (int)((avail - wbytes) / a_stage); nb = 0;                                                           \
+      } else {                                                                                                    \
+        na = 2; nb = (int)((avail - na * a_stage) / SM::kBTileBytes);                                             \
+        if (nb < 2) return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");             \
+      }                                                                                                           \
+      if (na > kMaxAStages) na = kMaxAStages;                                                                     \
+      if (nb > kMaxBStages) nb = kMaxBStages;                                                                     \
+      p.na_stages = na; p.nb_stages = nb; p.b_resident = res ? 1 : 0;                                             \
+      const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * SM::kBTileBytes) + SM::tail_bytes(); \
+      STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)smem_cap));                                                          \
+      conv_igemm_kernel<BN_><<<grid, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);                   \
+    } while (0)
+    if (bn_launch == 64) STP3_LAUNCH_CONV(64);
+    else STP3_LAUNCH_CONV(128);
 #undef STP3_LAUNCH_CONV
-  STP3_CUDA_OK(cudaGetLastError());
+    STP3_CUDA_OK(cudaGetLastError());
+  }
   return STP3_OK;
 }

@@ -100,8 +100,8 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     dev = weight.device
     taps, mats = [], []
     for it in range(kt):
-        for iy in range(kh):
-            for ix in range(kw):
+        for ix in range(kw):              # dy innermost: consecutive taps (dy, dy+1, dy+2) share one activation load
+            for iy in range(kh):
                 dy, dx = iy * dilation - pad_h, ix * dilation - pad_w
                 if prune_extent is not None and stride == 1:
                     # a tap whose shift exceeds the image reads only zero padding for every output pixel
