@@ -32,7 +32,7 @@ namespace stp3 {
 
 constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int kConvThreads = 64 + kEpiWarps * 32;
-constexpr int kTileH = 16, kTileW = 16;         // 256 output pixels = two UMMA M=128 sub-tiles (rows 0-7 and 8-15)
+constexpr int kSubH = 8, kTileW = 16;           // one UMMA M=128 sub-tile = 8 x 16 pixels; a tile stacks n_sub (1 or 2) of them
 constexpr int kBK = 64;                         // channels per K step (one 128-byte swizzle row of bf16)
 constexpr int kMaxTaps = 49;
 constexpr int kMaxAStages = 4, kMaxBStages = 8;
@@ -45,6 +45,7 @@ struct ConvParams {
   int kblocks;              // Cin / 64 of this convolution
   int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
   int ntaps;
+  int n_sub;                // sub-tiles per tile: 2 (16x16 pixels, weight tiles shared) or 1 (small images: more tiles)
   int group;                // taps that share one activation load: 3 = the three dy taps of a 3x3 (stride 1, dilation 1)
   int a_plane_bytes;        // bytes of one activation plane of a stage = box_h * 16 px * 128 B
   int w_rows;               // rows per (tap, kb, plane) block of the packed weight tensor (the convolution's padded Cout)
@@ -153,7 +154,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-        const int oy0 = (rem / p.tiles_x) * kTileH, ox0 = (rem % p.tiles_x) * kTileW;
+        const int oy0 = (rem / p.tiles_x) * (kSubH * p.n_sub), ox0 = (rem % p.tiles_x) * kTileW;
         const int bidx = img / p.T, tidx = p.t0 + img % p.T;
         for (int grp = 0; grp < n_groups; ++grp) {
           const int tap0 = grp * p.group;
@@ -210,8 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
               }
               const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + BN * kBK * 2);
-#pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
+              for (int sub = 0; sub < p.n_sub; ++sub) {
                 // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
                 const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
                 const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_hi + p.a_plane_bytes);
@@ -249,13 +249,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     int buf = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int oy_t = (rem / p.tiles_x) * kTileH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
+      const int oy_t = (rem / p.tiles_x) * (kSubH * p.n_sub), ox = (rem % p.tiles_x) * kTileW + (r & 15);
       const float* ib = p.img_bias ? p.img_bias + (size_t)img * p.img_bias_stride : nullptr;
       ptx::mbar_wait(&tmem_full_bar[buf], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int oy = oy_t + sub * 8 + (r >> 4);
+      for (int sub = 0; sub < p.n_sub; ++sub) {
+        const int oy = oy_t + sub * kSubH + (r >> 4);
         const bool valid = oy < p.Ho && ox < p.Wo;
         const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
         float hacc[kMaxHeadOut];
@@ -436,7 +436,12 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
             d->taps[i + j][1] != d->taps[i][1] + j)
           group = 1;
   }
-  const int box_h = kTileH + (group - 1);
+  // two sub-tiles per tile halve the weight traffic; small images keep one so that there are enough tiles
+  const int n_img_ = d->B * d->T;
+  const long long tiles16 = (long long)n_img_ * ceil_div(d->Wo, kTileW) * ceil_div(d->Ho, 2 * kSubH);
+  const int n_sub = tiles16 >= 3 * 148 ? 2 : 1;
+  const int tile_h = kSubH * n_sub;
+  const int box_h = tile_h + (group - 1);
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   {
@@ -472,7 +477,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 
   ConvParams p;
   p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
-  p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, kTileH);
+  p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
   p.group = group; p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }

@@ -79,7 +79,7 @@ class Decoder(PackedModule):
         c = self.in_channels
         cp = dense.pad_to(c)
         all_frames = [(k, getattr(self, attr)) for k, attr, present in self._HEADS if hasattr(self, attr) and not present]
-        groups, per = [], max(1, 256 // cp)
+        groups, per = [], max(1, 128 // cp)          # a fused-head convolution is at most 128 columns wide
         for i in range(0, len(all_frames), per):
             groups.append(self._pack_head_group(all_frames[i:i + per], c, cp))
         P["head_groups"] = groups

@@ -148,3 +148,14 @@ def test_encoder_heads_vs_reference_golden():
         r_hi, r_lo = dense_input((2, 160, 14, 30), 21).to(DEV), dense_input((2, 56, 28, 60), 22).to(DEV)
         y = u(h(r_hi), r_lo)
     close(y, torch.from_numpy(g["out"]))
+
+
+def test_temporal_model_receptive_field_5():
+    """Stress configuration: S=5 -> four TemporalBlocks (temporal_model.py:13)."""
+    H, W = 16, 24
+    with torch.no_grad():
+        tm = TD.init_exact(TemporalModel(70, 5, (H, W), start_out_channels=64), seed=13).eval()
+        x = dense_input((1, 5, 70, H, W), 14)
+        ref = TD.temporal_model(x.double(), f64(tm))
+        y = tm.to(DEV)(x.to(DEV))
+    close(y, ref)

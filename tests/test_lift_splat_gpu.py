@@ -160,3 +160,23 @@ def test_workspace_clean_after_pool_sum_call_of_another_shape():
     cfg2, inp2, g2 = load_lift_case("tiny_randpose")
     out = run_cuda(cfg2, inp2, g2, workspace=ws)
     assert_bev_close(out.cpu().numpy(), run_oracle(cfg2, inp2, g2)["bev"])
+
+
+def test_stress_like_shapes_c128_d96_s5():
+    """BASELINE configs[4] in miniature: C=128 (two 64-channel chunks in the scatter, two channel groups in the
+    finalize), D=96 depth bins, S=5 frames (four chained ego poses), ranks bit-exact and BEV within tolerance."""
+    cfg = syn.LiftSplatConfig(x_bound=(-20.0, 20.0, 0.5), y_bound=(-20.0, 20.0, 0.5), d_bound=(2.0, 98.0, 1.0),
+                              final_dim=(64, 96), out_channels=128, n_cameras=3, receptive_field=5)
+    inp = syn.lift_inputs(cfg, 2, seed=9, random_pose=True)
+    cam_M, cam_t, ego_R, ego_t = G.lift_matrices(inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+    xs, ys, ds = G.frustum_axes(cfg.final_dim, cfg.downsample, cfg.d_bound)
+    res, start, dim = G.calculate_birds_eye_view_parameters(cfg.x_bound, cfg.y_bound, cfg.z_bound)
+    g = dict(cam_M=cam_M.numpy(), cam_t=cam_t.numpy(), ego_R=ego_R.numpy(), ego_t=ego_t.numpy(), xs=xs.numpy(),
+             ys=ys.numpy(), ds=ds.numpy(), bev_offset=G.bev_offset(start, res).numpy(), bev_resolution=res.numpy(),
+             bev_dimension=dim.numpy())
+    out, ranks, psum = run_cuda(cfg, inp, g, return_ranks=True, pool_sum=True)
+    ora = run_oracle(cfg, inp, g)
+    assert np.array_equal(ranks.cpu().numpy(), ora["rank"])
+    assert_bev_close(out.cpu().numpy(), ora["bev"])
+    tot = ora["bev"].sum(axis=(-1, -2))
+    assert np.allclose(psum.cpu().numpy(), tot, rtol=1e-4, atol=1e-4 * np.abs(tot).max())
