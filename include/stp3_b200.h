@@ -125,6 +125,8 @@ typedef struct stp3_conv_desc {
   int res_cstride, res_coff;
   int n_valid;           /* real output channels written to y_f32 */
   int sigmoid;           /* apply a sigmoid to y_f32 (instance_center head, decoder.py:70) */
+  int tune_n_sub;        /* 0 = automatic; 1 / 2 = sub-tiles (8x16 pixels each) per CTA tile */
+  int tune_group;        /* 0 = automatic; 1 = never share an activation load between the dy taps of a 3x3 */
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:

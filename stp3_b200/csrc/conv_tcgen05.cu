@@ -426,9 +426,14 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   PFN_tmapEncodeTiled enc = encode_fn();
   if (!enc) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
 
+  // tuning knobs (0 = automatic): desc->tune_n_sub / tune_group, or the STP3_CONV_NSUB / STP3_CONV_GROUP environment
+  static const int env_nsub = [] { const char* e = getenv("STP3_CONV_NSUB"); return e ? atoi(e) : 0; }();
+  static const int env_group = [] { const char* e = getenv("STP3_CONV_GROUP"); return e ? atoi(e) : 0; }();
+  const int want_nsub = d->tune_n_sub ? d->tune_n_sub : env_nsub;
+  const int want_group = d->tune_group ? d->tune_group : env_group;
   // taps that can share one activation load: consecutive triples (same dt, dx; dy, dy+1, dy+2) of a stride-1 kernel
   int group = 1;
-  if (d->stride == 1 && d->ntaps % 3 == 0) {
+  if (d->stride == 1 && d->ntaps % 3 == 0 && want_group != 1) {
     group = 3;
     for (int i = 0; i < d->ntaps && group == 3; i += 3)
       for (int j = 1; j < 3; ++j)
@@ -439,7 +444,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   // two sub-tiles per tile halve the weight traffic; small images keep one so that there are enough tiles
   const int n_img_ = d->B * d->T;
   const long long tiles16 = (long long)n_img_ * ceil_div(d->Wo, kTileW) * ceil_div(d->Ho, 2 * kSubH);
-  const int n_sub = tiles16 >= 3 * 148 ? 2 : 1;
+  const int n_sub = want_nsub == 1 || want_nsub == 2 ? want_nsub : (tiles16 >= 3 * 148 ? 2 : 1);
   const int tile_h = kSubH * n_sub;
   const int box_h = tile_h + (group - 1);
 
@@ -528,8 +533,14 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       if (res) {                                                                                                  \
         na = (int)((avail - wbytes) / a_stage); nb = 0;                                                           \
       } else {                                                                                                    \
-        na = 2; nb = (int)((avail - na * a_stage) / SM::kBTileBytes);                                             \
-        if (nb < 2) return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");             \
+        /* as many activation stages as fit beside max(2, group) weight slots, then fill up with weight slots */  \
+        const int nb_min = group > 2 ? group : 2;                                                                 \
+        na = (int)((avail - (size_t)nb_min * SM::kBTileBytes) / a_stage);                                         \
+        if (na < 2) na = 2;                                                                                       \
+        if (na > kMaxAStages) na = kMaxAStages;                                                                   \
+        if ((size_t)na * a_stage + 2 * SM::kBTileBytes > avail)                                                   \
+          return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");                       \
+        nb = (int)((avail - (size_t)na * a_stage) / SM::kBTileBytes);                                             \
       }                                                                                                           \
       if (na > kMaxAStages) na = kMaxAStages;                                                                     \
       if (nb > kMaxBStages) nb = kMaxBStages;                                                                     \
