@@ -141,9 +141,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   const int n_groups = p.ntaps / p.group;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (resident) {
+    // ===================== TMA producer (whole warp walks the loops; one elected lane issues) =====================
+    {
+      if (resident && ptx::elect_one_sync()) {
         ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
         for (int it = 0; it < k_iters; ++it) {
           unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
@@ -151,6 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           ptx::tma_load_2d(dst + BN * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
         }
       }
+      __syncwarp();
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
@@ -163,20 +164,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           const int t = tidx + p.tap[tap0][0];
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&a_empty[as], aph ^ 1);
-            unsigned char* sa = a_ring + (size_t)as * a_stage_bytes;
-            ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
-            const int c = p.cin_off + kb * kBK;
-            ptx::tma_load_5d(sa, &tm_a_hi, &a_full[as], c, x, y, t, bidx);
-            ptx::tma_load_5d(sa + p.a_plane_bytes, &tm_a_lo, &a_full[as], c, x, y, t, bidx);
+            if (ptx::elect_one_sync()) {
+              unsigned char* sa = a_ring + (size_t)as * a_stage_bytes;
+              ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
+              const int c = p.cin_off + kb * kBK;
+              ptx::tma_load_5d(sa, &tm_a_hi, &a_full[as], c, x, y, t, bidx);
+              ptx::tma_load_5d(sa + p.a_plane_bytes, &tm_a_lo, &a_full[as], c, x, y, t, bidx);
+            }
+            __syncwarp();
             if (++as == p.na_stages) { as = 0; aph ^= 1; }
             if (!resident) {
               for (int j = 0; j < p.group; ++j) {
                 const int it = (tap0 + j) * p.kblocks + kb;          // [tap][kb][plane][rows] blocks of 64-wide rows
                 ptx::mbar_wait(&b_empty[bs], bph ^ 1);
-                unsigned char* sb = b_ring + (size_t)bs * S::kBTileBytes;
-                ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
-                ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + p.w_row_off);
-                ptx::tma_load_2d(sb + BN * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
+                if (ptx::elect_one_sync()) {
+                  unsigned char* sb = b_ring + (size_t)bs * S::kBTileBytes;
+                  ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
+                  ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + p.w_row_off);
+                  ptx::tma_load_2d(sb + BN * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
+                }
+                __syncwarp();
                 if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
               }
             }
@@ -185,8 +192,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
       if (resident) ptx::mbar_wait(bres_bar, 0);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
@@ -211,6 +218,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
               }
               const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + BN * kBK * 2);
+              if (ptx::elect_one_sync()) {
               for (int sub = 0; sub < p.n_sub; ++sub) {
                 // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
                 const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
@@ -224,17 +232,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   ptx::umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
                 }
               }
-              accumulate = 1;
-              if (!resident) {
-                ptx::umma_commit(&b_empty[bs]);      // frees the weight slot when these MMAs have read it
-                if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
+              if (!resident) ptx::umma_commit(&b_empty[bs]);      // frees the weight slot when these MMAs have read it
               }
+              __syncwarp();
+              accumulate = 1;
+              if (!resident) { if (++bs == p.nb_stages) { bs = 0; bph ^= 1; } }
             }
-            ptx::umma_commit(&a_empty[as]);          // frees the activation slot
+            if (ptx::elect_one_sync()) ptx::umma_commit(&a_empty[as]);          // frees the activation slot
+            __syncwarp();
             if (++as == p.na_stages) { as = 0; aph ^= 1; }
           }
         }
-        ptx::umma_commit(&tmem_full_bar[buf]);       // accumulators complete -> epilogue
+        if (ptx::elect_one_sync()) ptx::umma_commit(&tmem_full_bar[buf]);       // accumulators complete -> epilogue
+        __syncwarp();
         if (++buf == 2) { buf = 0; acc_phase ^= 1; }
       }
     }

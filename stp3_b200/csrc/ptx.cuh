@@ -15,6 +15,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return r;
 }
 
+// true in exactly one (elected) lane of a converged warp.  Code guarded by it may use the uniform datapath
+// (UTCHMMA / UTMALDG / UTCBAR are uniform instructions): guarding them with `lane == 0` instead makes the compiler
+// wrap every one of them in an elect-and-retry loop (~7 SASS instructions per MMA, which throttles N=64 MMAs).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
