@@ -366,6 +366,10 @@ def main():
         else:
             line["gpu_launches"] = 2 * K * 2
             line["roofline"] = roof_ls
+        if perceive and os.environ.get("STP3_TUNE_REPORT"):
+            from stp3_b200 import dense
+            for desc, times in dense.TUNE_LOG:
+                print("TUNE", desc.ljust(44), "  ".join(f"{k}:{v * 1e3:7.1f}us" for k, v in times.items()), file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
             fps, dt, threads = time_reference(args.workload, cfg, 1, 0)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",

@@ -124,6 +124,36 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     return PackedConv(packed, b, taps, cin_p, bn, cout, stride)
 
 
+# ------------------------------------------------------------------------------------------------ autotuner
+# The conv kernel has two tiling knobs (sub-tiles per CTA tile, sharing one activation load between the dy taps of a
+# 3x3).  Which combination wins depends on the layer (K depth, N width, image size, whether the weights are
+# smem-resident), so the first eager call of every (layer, shape) times the candidates back to back and the winner is
+# cached; CUDA-graph capture then records the tuned launches.  STP3_CONV_AUTOTUNE=0 disables it (kernel heuristics).
+import os as _os
+
+_TUNED = {}
+_AUTOTUNE = _os.environ.get("STP3_CONV_AUTOTUNE", "1") != "0"
+TUNE_LOG = []      # (description, {config: ms}) for reports
+
+
+def _tune(key, desc, launch, groupable):
+    cands = [(1, 1), (2, 1)] + ([(1, 3), (2, 3)] if groupable else [])
+    times = {}
+    for ns, g in cands:
+        launch(ns, g)                                   # warm (descriptor / attribute setup)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            launch(ns, g)
+        b.record()
+        b.synchronize()
+        times[(ns, g)] = a.elapsed_time(b) / 4
+    best = min(times, key=times.get)
+    _TUNED[key] = best
+    TUNE_LOG.append((desc, times))
+    return best
+
+
 def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, out_coff: int = 0, relu: bool = False,
          img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
@@ -170,13 +200,28 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         assert img_bias.shape == (B * T, pc.bn) and img_bias.dtype == torch.float32 and img_bias.is_contiguous()
     dev = x.hi.device
     ptr = lambda t: t.data_ptr() if t is not None else None
-    with torch.cuda.device(dev):
-        code = _lib.lib().stp3_conv_fwd(
-            ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), ptr(img_bias),
-            ptr(residual.hi if residual is not None else None), ptr(residual.lo if residual is not None else None),
-            ptr(out.hi if out is not None else None), ptr(out.lo if out is not None else None), ptr(out_f32),
-            ctypes.byref(hd) if hd is not None else None, torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(code, "stp3_conv_fwd")
+
+    def launch(n_sub=0, group=0):
+        d.tune_n_sub, d.tune_group = n_sub, group
+        with torch.cuda.device(dev):
+            code = _lib.lib().stp3_conv_fwd(
+                ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), ptr(img_bias),
+                ptr(residual.hi if residual is not None else None), ptr(residual.lo if residual is not None else None),
+                ptr(out.hi if out is not None else None), ptr(out.lo if out is not None else None), ptr(out_f32),
+                ctypes.byref(hd) if hd is not None else None, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(code, "stp3_conv_fwd")
+
+    key = (pc.w.data_ptr(), B, T, H, W, cs, cin_off, Ho, Wo, t0, int(relu), residual is not None, out_f32 is not None,
+           hd is not None)
+    cfg = _TUNED.get(key)
+    if cfg is None and _AUTOTUNE and not torch.cuda.is_current_stream_capturing():
+        taps = pc.taps
+        groupable = pc.stride == 1 and len(taps) % 3 == 0 and all(
+            taps[i + j][0] == taps[i][0] and taps[i + j][2] == taps[i][2] and taps[i + j][1] == taps[i][1] + j
+            for i in range(0, len(taps), 3) for j in (1, 2))
+        desc = f"{len(taps)}tap cin{pc.cin_p} bn{pc.bn} s{pc.stride} {B * T}x{Ho}x{Wo}"
+        cfg = _tune(key, desc, launch, groupable)
+    launch(*(cfg or (0, 0)))
     return out
 
 
