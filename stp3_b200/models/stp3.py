@@ -240,3 +240,67 @@ class GraphedPerception:
         self.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class PipelinedPerception:
+    """Throughput front-end for host-resident inputs: `depth` GraphedPerception slots, host->device copies of step
+    i+1 and device->host copies of step i-1 run on copy streams while step i replays its CUDA graph.
+
+        pipe = PipelinedPerception(model, batch, n_cameras)
+        pipe.submit(feat, depth_logits, intrinsics, extrinsics, future_egomotion)      # pinned host tensors
+        ...                                                                            # (submit up to `depth` steps)
+        out = pipe.collect()        # oldest outstanding step: dict of pinned host tensors (reused every `depth` steps)
+    """
+
+    def __init__(self, model: STP3, batch: int, n_cameras: int, depth: int = 2, device=None,
+                 keys=("segmentation", "pedestrian", "hdmap")):
+        self.model = model
+        dev = torch.device(device) if device is not None else next(model.parameters()).device
+        self.dev = dev
+        self.slots = [GraphedPerception(model, batch, n_cameras, dev) for _ in range(depth)]
+        self.keys = [k for k in keys if self.slots[0].out.get(k) is not None]
+        self.host_out = [{k: torch.empty(sl.out[k].shape, dtype=torch.float32).pin_memory() for k in self.keys}
+                         for sl in self.slots]
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in self.slots]
+        self.ev_done = [torch.cuda.Event() for _ in self.slots]
+        self.ev_out = [torch.cuda.Event() for _ in self.slots]
+        self.head = self.tail = self.inflight = 0
+        self.between_steps = None      # optional callable enqueued on the compute stream before every replay
+
+    def submit(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        assert self.inflight < len(self.slots), "collect() a finished step before submitting another one"
+        i = self.head
+        sl = self.slots[i]
+        S = self.model.receptive_field
+        host = self.model.prepare_inputs(intrinsics, extrinsics, future_egomotion)
+        compute = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.ev_done[i])          # the slot's previous replay has consumed its inputs
+            for k, v in host.items():
+                sl.pinned[k].copy_(v)
+                sl.static[k].copy_(sl.pinned[k], non_blocking=True)
+            sl.static["feat"].copy_(feat[:, :S], non_blocking=True)
+            sl.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
+            self.ev_in[i].record(self.copy_in)
+        compute.wait_event(self.ev_in[i])
+        compute.wait_event(self.ev_out[i])                    # the slot's previous outputs have left the device
+        if self.between_steps is not None:
+            self.between_steps()
+        sl.graph.replay()
+        self.ev_done[i].record(compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.ev_done[i])
+            for k in self.keys:
+                self.host_out[i][k].copy_(sl.out[k], non_blocking=True)
+            self.ev_out[i].record(self.copy_out)
+        self.head = (i + 1) % len(self.slots)
+        self.inflight += 1
+
+    def collect(self):
+        assert self.inflight > 0
+        i = self.tail
+        self.ev_out[i].synchronize()
+        self.tail = (i + 1) % len(self.slots)
+        self.inflight -= 1
+        return self.host_out[i]

@@ -112,3 +112,31 @@ def test_cuda_graph_replay_equals_eager():
             for k in ("segmentation", "pedestrian", "hdmap"):
                 # identical kernels and launch order; only the lift-splat's atomic summation order may differ
                 assert (out[k] - eager[k]).abs().max() <= 1e-4 * eager[k].abs().max(), k
+
+
+def test_pipelined_front_end_matches_eager():
+    """PipelinedPerception (copies overlapped with graph replays, two slots) returns the eager results in order."""
+    from stp3_b200.models.stp3 import PipelinedPerception
+    cfg = small_cfg()
+    lcfg = syn.LiftSplatConfig(x_bound=(-8.0, 8.0, 0.5), y_bound=(-8.0, 8.0, 0.5), d_bound=(2.0, 10.0, 1.0),
+                               final_dim=(32, 48), out_channels=64, n_cameras=2, receptive_field=3)
+    with torch.no_grad():
+        model = syn.init_exact(STP3(cfg, backbone=FakeTrunk()), seed=8).eval()
+        model.frustum.copy_(model.create_frustum())
+        res, start, dim = G.calculate_birds_eye_view_parameters(cfg.LIFT.X_BOUND, cfg.LIFT.Y_BOUND, cfg.LIFT.Z_BOUND)
+        model.bev_resolution.copy_(res); model.bev_start_position.copy_(start); model.bev_dimension.copy_(dim)
+        model = model.to(DEV)
+        pipe = PipelinedPerception(model, 2, 2)
+        inputs = [syn.lift_inputs(lcfg, 2, seed=s, random_pose=True) for s in (1, 2, 3)]
+        pinned = [{k: v.pin_memory() for k, v in i.items()} for i in inputs]
+        got = []
+        for k, h in enumerate(pinned):
+            pipe.submit(h["feat"], h["depth_logits"], h["intrinsics"], h["extrinsics"], h["future_egomotion"])
+            if k >= 1:
+                got.append({key: t.clone() for key, t in pipe.collect().items()})
+        got.append({key: t.clone() for key, t in pipe.collect().items()})
+        for inp, out in zip(inputs, got):
+            eager = model.forward_features(inp["feat"].to(DEV), inp["depth_logits"].to(DEV), inp["intrinsics"],
+                                           inp["extrinsics"], inp["future_egomotion"])
+            for key in ("segmentation", "pedestrian", "hdmap"):
+                assert (out[key] - eager[key].cpu()).abs().max() <= 1e-4 * eager[key].abs().max(), key
