@@ -227,6 +227,9 @@ def main():
         return
 
     from stp3_b200 import ops
+    # the host side of a step is a few hundred floats of calibration math (torch.inverse etc.); with the default
+    # 64-128 intra-op threads every such call pays a multi-millisecond OpenMP wake-up, so keep the pool small
+    torch.set_num_threads(min(4, os.cpu_count() or 1))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -399,7 +402,7 @@ def main():
             for desc, times in dense.TUNE_LOG:
                 print("TUNE", desc.ljust(44), "  ".join(f"{k}:{v * 1e3:7.1f}us" for k, v in times.items()), file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
-            fps, dt, threads = time_reference(args.workload, cfg, 1, 0)
+            fps, dt, threads = time_reference(args.workload, cfg, 1, 0)       # picks its own (best) thread count
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 sample through the op-for-op CPU port of the reference (oracle/torch_port.py"
                                               f"{' + oracle/torch_dense.py' if perceive else ''}), 1 run, {threads} threads"}
