@@ -21,8 +21,11 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace stp3 {
 
@@ -334,6 +337,277 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (the fast path: 4-column tiles, Wf % 4 == 0).  Same phases and the same arithmetic as
+// lift_splat_scatter_kernel, but the tile's depth logits and context features are fetched by the TMA unit
+// (cp.async.bulk.tensor, 3-D boxes) the moment the CTA starts, and the pure-ALU rank computation (phase B) runs while
+// they are in flight; nothing in the kernel waits on a global load except the two mbarrier waits.
+//   logits   box (4 w, Hf, D)      -> s_stage [D][Hf][4]            (softmax transposes it into s_prob [D][4][HP])
+//   features NCHW: 8 boxes (4 w, Hf, 8 ch) -> s_feat[g][8][Hf][4] with a group stride == 4 (mod 32) floats
+//            NHWC: 1 box (64 ch, 4 w, Hf)  -> s_feat[Hf][4][64]
+constexpr int kTmaTW = 4;
+
+struct LiftSplatTmaMaps {
+  CUtensorMap depth;   // (Wf, Hf, D * n_img) fp32
+  CUtensorMap feat;    // NCHW: (Wf, Hf, C * n_img) fp32 ; NHWC: (C, Wf, Hf * n_img) fp32
+};
+
+__device__ __forceinline__ int feat_index_nchw(int cl, int h, int wl, int Hf, int gstride) {
+  return (cl >> 3) * gstride + (cl & 7) * Hf * kTmaTW + h * kTmaTW + wl;
+}
+
+__global__ void __launch_bounds__(kScatterThreads, 2)
+lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, const LiftSplatParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((128u - (ptx::smem_u32(smem_dyn) & 127u)) & 127u);
+  constexpr int TW = kTmaTW;
+  const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C;
+  const int HP = (Hf + 3) & ~3;
+  const int npix = Hf * TW;
+  const int gstride = ((8 * npix + 31) & ~31) + 4;                 // floats between 8-channel groups (== 4 mod 32)
+  const int feat_floats = p.feat_nhwc ? npix * kCChunk : 8 * gstride;
+  float* s_stage = reinterpret_cast<float*>(smem_raw);             // [D][Hf][TW] raw logits (TMA destination)
+  float* s_feat = s_stage + ((D * npix + 31) & ~31);               // feature tile (TMA destination)
+  float* s_prob = s_feat + ((feat_floats + 31) & ~31);             // [D][TW][HP]
+  int* s_rank = reinterpret_cast<int*>(s_prob + D * TW * HP);      // [D][TW][HP]
+  int* s_col = s_rank + D * TW * HP;                               // [D][TW]
+  float* s_mat = reinterpret_cast<float*>(s_col + D * TW);         // camera 12 + (kMaxFrames-1) * 12 pose floats
+  float* s_ys = s_mat + 12 * kMaxFrames;
+  float* s_ds = s_ys + Hf;
+  float* s_red = s_ds + D;                                         // [blockDim]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + kScatterThreads + (((Hf + D) & 1) ? 1 : 0));
+
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  int blk = blockIdx.x;
+  const int tile = blk % p.tiles_w; blk /= p.tiles_w;
+  const int n = blk % p.N; blk /= p.N;
+  const int t = blk % p.S;
+  const int b = blk / p.S;
+  const int w0 = tile * TW;
+  const int img = (b * p.S + t) * p.N + n;
+  const int bt = b * p.S + t;
+  const int n_chain = p.S - 1 - t;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_features = [&](int c0) {     // one thread: arm the barrier and start the feature tile of channels [c0, c0+64)
+    if (p.feat_nhwc) {
+      ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(npix * kCChunk * 4));
+      ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], c0, w0, img * Hf);
+    } else {
+      ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(kCChunk * npix * 4));
+      for (int g = 0; g < 8; ++g)
+        ptx::tma_load_3d(s_feat + g * gstride, &maps.feat, &bars[1], w0, 0, img * C + c0 + 8 * g);
+    }
+  };
+  if (tid == 0) {
+    if (p.use_depth) {
+      ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)(D * npix * 4));
+      ptx::tma_load_3d(s_stage, &maps.depth, &bars[0], w0, 0, img * D);
+    }
+    issue_features(0);
+  }
+
+  const int npix_r = (npix + 31) & ~31;
+  const int parts = max(1, nthr / npix_r);
+  const int my_part = (nthr / npix_r) <= 1 ? 0 : tid / npix_r;
+  const int dchunk = (D + parts - 1) / parts;
+
+  if (tid < 9) s_mat[tid] = p.cam_M[img * 9 + tid];
+  if (tid >= 9 && tid < 12) s_mat[tid] = p.cam_t[img * 3 + tid - 9];
+  for (int i = tid; i < n_chain * 12; i += nthr) {
+    const int k = i / 12, e = i % 12;
+    const int src = b * p.S + t + k;
+    s_mat[12 + i] = e < 9 ? p.ego_R[src * 9 + e] : p.ego_t[src * 3 + e - 9];
+  }
+  for (int i = tid; i < Hf; i += nthr) s_ys[i] = p.ys[i];
+  for (int i = tid; i < D; i += nthr) s_ds[i] = p.ds[i];
+  if (HP != Hf)
+    for (int i = tid; i < D * TW * (HP - Hf); i += nthr) {
+      const int col = i / (HP - Hf), r = i % (HP - Hf);
+      s_prob[col * HP + Hf + r] = 0.f;
+      s_rank[col * HP + Hf + r] = -1;
+    }
+  __syncthreads();
+
+  // ---- phase B (pure ALU, overlaps the TMA transfers): voxel rank of every point, bit-exact with the reference
+  const float offx = p.off[0], offy = p.off[1], offz = p.off[2];
+  const float resx = p.res[0], resy = p.res[1], resz = p.res[2];
+  const float fnx = (float)p.nx, fny = (float)p.ny, fnz = (float)p.nz;
+  for (int px0 = 0; px0 < npix; px0 += (parts == 1 ? nthr : npix_r)) {
+    const int px = px0 + (parts == 1 ? tid : tid % npix_r);
+    const bool act = px < npix && my_part < parts;
+    if (!act) continue;
+    const int wl = px % TW, h = px / TW;
+    const int w = w0 + wl;
+    const bool inb = w < Wf;
+    const int da = my_part * dchunk, db = min(D, da + dchunk);
+    int* rrow = s_rank + wl * HP + h;
+    const float xw = inb ? __ldg(p.xs + w) : 0.f;
+    const float yh = s_ys[h];
+    for (int d = da; d < db; ++d) {
+      int rank = -1;
+      if (inb) {
+        const float dep = s_ds[d];
+        float x = __fmul_rn(xw, dep);                  // stp3.py:195: (u*d, v*d, d)
+        float y = __fmul_rn(yh, dep);
+        float z = dep;
+        affine_exact(s_mat, s_mat + 9, x, y, z);       // stp3.py:196-198
+        for (int k = 0; k < n_chain; ++k)              // stp3.py:270-277, sequential, rounded every step
+          affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
+        const float qx = p.inv_ok[0] ? __fmul_rn(__fsub_rn(x, offx), p.inv[0]) : __fdiv_rn(__fsub_rn(x, offx), resx);
+        const float qy = p.inv_ok[1] ? __fmul_rn(__fsub_rn(y, offy), p.inv[1]) : __fdiv_rn(__fsub_rn(y, offy), resy);
+        const float qz = p.inv_ok[2] ? __fmul_rn(__fsub_rn(z, offz), p.inv[2]) : __fdiv_rn(__fsub_rn(z, offz), resz);
+        const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
+        if (keep) {
+          const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi == .long() truncation
+          rank = ix * (p.ny * p.nz) + iy * p.nz + iz;              // stp3.py:251-255
+        }
+        if (p.ranks_out) p.ranks_out[(((size_t)img * D + d) * Hf + h) * Wf + w] = rank;
+      }
+      rrow[d * TW * HP] = rank;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase A: softmax over D of the TMA-landed logits, written transposed ([d][wl][h]) with masked points zeroed
+  if (p.use_depth) ptx::mbar_wait(&bars[0], 0);
+  for (int px0 = 0; px0 < npix; px0 += (parts == 1 ? nthr : npix_r)) {
+    const int px = px0 + (parts == 1 ? tid : tid % npix_r);
+    const bool act = px < npix && my_part < parts;
+    const int wl = px % TW, h = px / TW;
+    const int da = my_part * dchunk, db = act ? min(D, da + dchunk) : da;
+    const float* srow = s_stage + px;               // + d*npix   ([d][h][w], px = h*TW + wl)
+    float* prow = s_prob + wl * HP + h;             // + d*TW*HP
+    const int* rrow = s_rank + wl * HP + h;
+    if (p.use_depth) {
+      float mx = -INFINITY;
+      for (int d = da; d < db; ++d) mx = fmaxf(mx, srow[d * npix]);
+      if (parts > 1) {
+        s_red[tid] = mx;
+        __syncthreads();
+        if (act) for (int q = 0; q < parts; ++q) mx = fmaxf(mx, s_red[q * npix_r + px - px0]);
+        __syncthreads();
+      }
+      float sum = 0.f;
+      for (int d = da; d < db; ++d) {
+        const float e = __expf(srow[d * npix] - mx);
+        prow[d * TW * HP] = e;
+        sum += e;
+      }
+      if (parts > 1) {
+        s_red[tid] = sum;
+        __syncthreads();
+        sum = 0.f;
+        if (act) for (int q = 0; q < parts; ++q) sum += s_red[q * npix_r + px - px0];
+        __syncthreads();
+      }
+      const float inv = __frcp_rn(sum);
+      for (int d = da; d < db; ++d) prow[d * TW * HP] = rrow[d * TW * HP] < 0 ? 0.f : prow[d * TW * HP] * inv;
+    } else {
+      for (int d = da; d < db; ++d) prow[d * TW * HP] = rrow[d * TW * HP] < 0 ? 0.f : 1.0f;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < D * TW; i += nthr) {       // column summary: one thread per (d, wl)
+    const int* r = s_rank + i * HP;
+    int first = -1;
+    bool uni = true;
+    for (int h = 0; h < Hf; ++h) {
+      const int v = r[h];
+      if (v >= 0) { uni &= (first < 0 || v == first); first = v; }
+    }
+    s_col[i] = uni ? first : -2;
+  }
+  __syncthreads();
+
+  // ---- phase C: outer product + segmented pooling (see lift_splat_scatter_kernel)
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nwarps = nthr >> 5;
+  const int dsplit = max(1, nwarps / TW);
+  const int dper = (D + dsplit - 1) / dsplit;
+  const size_t nvox = (size_t)p.nx * p.ny * p.nz;
+  float* gbase = p.grid + (size_t)bt * nvox * C;
+  unsigned char* obase = p.occ + (size_t)bt * nvox;
+  const bool vec_ok = (C % 2) == 0;
+  uint32_t fphase = 0;
+  for (int c0 = 0; c0 < C; c0 += kCChunk) {
+    ptx::mbar_wait(&bars[1], fphase);
+    fphase ^= 1;
+    const int c = c0 + 2 * lane;
+    const bool mark = (lane == 0) && (c0 == 0);
+    for (int item = warp; item < TW * dsplit; item += nwarps) {
+      const int wl = item % TW;
+      if (w0 + wl >= Wf) continue;
+      const int d0 = (item / TW) * dper;
+      const int d1 = min(D, d0 + dper);
+      for (int h0 = 0; h0 < Hf; h0 += kHChunk) {
+        float f0[kHChunk], f1[kHChunk];
+#pragma unroll
+        for (int j = 0; j < kHChunk; ++j) {
+          const int h = h0 + j;
+          f0[j] = 0.f; f1[j] = 0.f;
+          if (h < Hf) {
+            if (p.feat_nhwc) {
+              const float2 v = *reinterpret_cast<const float2*>(s_feat + (h * TW + wl) * kCChunk + 2 * lane);
+              f0[j] = v.x; f1[j] = v.y;
+            } else {
+              f0[j] = s_feat[feat_index_nchw(2 * lane, h, wl, Hf, gstride)];
+              f1[j] = s_feat[feat_index_nchw(2 * lane + 1, h, wl, Hf, gstride)];
+            }
+          }
+        }
+        for (int d = d0; d < d1; ++d) {
+          const int col = s_col[d * TW + wl];
+          if (col == -1) continue;                   // the whole column is outside the grid
+          const float* pr = s_prob + (d * TW + wl) * HP + h0;
+          if (col >= 0) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < kHChunk / 4; ++j4) {
+              if (h0 + 4 * j4 < Hf) {
+                const float4 q = *reinterpret_cast<const float4*>(pr + 4 * j4);
+                a0 = fmaf(q.x, f0[4 * j4 + 0], a0); a1 = fmaf(q.x, f1[4 * j4 + 0], a1);
+                a0 = fmaf(q.y, f0[4 * j4 + 1], a0); a1 = fmaf(q.y, f1[4 * j4 + 1], a1);
+                a0 = fmaf(q.z, f0[4 * j4 + 2], a0); a1 = fmaf(q.z, f1[4 * j4 + 2], a1);
+                a0 = fmaf(q.w, f0[4 * j4 + 3], a0); a1 = fmaf(q.w, f1[4 * j4 + 3], a1);
+              }
+            }
+            flush_segment(gbase, obase, col, C, c, vec_ok, mark, a0, a1);
+          } else {
+            const int* rk = s_rank + (d * TW + wl) * HP + h0;
+            int cur = -1;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kHChunk; ++j) {
+              if (h0 + j < Hf) {
+                const int r = rk[j];
+                if (r != cur) {
+                  if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
+                  cur = r; a0 = 0.f; a1 = 0.f;
+                }
+                const float q = pr[j];
+                a0 = fmaf(q, f0[j], a0);
+                a1 = fmaf(q, f1[j], a1);
+              }
+            }
+            if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
+          }
+        }
+      }
+    }
+    if (c0 + kCChunk < C) {              // next 64 channels: the tile buffer is free once every warp is done with it
+      __syncthreads();
+      if (tid == 0) issue_features(c0 + kCChunk);
+    }
+  }
+}
+
 // out[b,t] = out[b,t-1]*discount + grid[b,t]  (stp3.py:296, separate fp32 mul and add like the reference's
 // `bev_feature * discount + tmp`).  One CTA = 32 consecutive pillars of one sample; lane = pillar, warp = a group
 // of 8 channels, so every global store of the (C, X*Y) output is a fully coalesced 128-byte row segment and no
@@ -500,6 +774,21 @@ __global__ void clear_bytes_kernel(unsigned char* __restrict__ p, size_t n) {
 
 using namespace stp3;
 
+typedef CUresult (*PFN_tmapEncode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncode tmap_encode_fn() {
+  static PFN_tmapEncode fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncode>(ptr);
+  }
+  return fn;
+}
+
 static size_t grid_bytes(int B, int S, int C, int nx, int ny) {
   const size_t g = (size_t)B * S * nx * ny * C * sizeof(float);
   return (g + 255) & ~(size_t)255;
@@ -583,8 +872,67 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
     STP3_CUDA_OK(cudaGetLastError());
     return STP3_OK;
   };
-  int rc = TW == 4 ? launch(lift_splat_scatter_kernel<4>)
-         : TW == 2 ? launch(lift_splat_scatter_kernel<2>) : launch(lift_splat_scatter_kernel<1>);
+  // fast path: TMA-staged tiles (needs 16-byte aligned rows for the tensor maps)
+  static const int no_tma = [] { const char* e = getenv("STP3_LIFT_NO_TMA"); return e ? atoi(e) : 0; }();
+  const bool tma_ok = !no_tma && TW == 4 && Wf % 4 == 0 && (feat_layout == 0 || C % 4 == 0) && D <= 256 && Hf <= 256 &&
+                      (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
+                      (!depth_logits || (reinterpret_cast<uintptr_t>(depth_logits) & 15) == 0);
+  int rc = STP3_OK;
+  bool used_tma = false;
+  if (tma_ok) {
+    PFN_tmapEncode enc = tmap_encode_fn();
+    if (enc) {
+      LiftSplatTmaMaps maps;
+      const long long n_img = (long long)B * S * N;
+      CUresult r1 = CUDA_SUCCESS, r2;
+      if (use_depth_distribution) {
+        const cuuint64_t dims[3] = {(cuuint64_t)Wf, (cuuint64_t)Hf, (cuuint64_t)(D * n_img)};
+        const cuuint64_t strides[2] = {(cuuint64_t)Wf * 4, (cuuint64_t)Hf * Wf * 4};
+        const cuuint32_t box[3] = {4, (cuuint32_t)Hf, (cuuint32_t)D};
+        const cuuint32_t es[3] = {1, 1, 1};
+        r1 = enc(&maps.depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(depth_logits), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        memset(&maps.depth, 0, sizeof(maps.depth));
+      }
+      if (feat_layout == 0) {
+        const cuuint64_t dims[3] = {(cuuint64_t)Wf, (cuuint64_t)Hf, (cuuint64_t)(C * n_img)};
+        const cuuint64_t strides[2] = {(cuuint64_t)Wf * 4, (cuuint64_t)Hf * Wf * 4};
+        const cuuint32_t box[3] = {4, (cuuint32_t)Hf, 8};
+        const cuuint32_t es[3] = {1, 1, 1};
+        r2 = enc(&maps.feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Wf, (cuuint64_t)(Hf * n_img)};
+        const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)Wf * C * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(C < kCChunk ? C : kCChunk), 4, (cuuint32_t)Hf};
+        const cuuint32_t es[3] = {1, 1, 1};
+        r2 = enc(&maps.feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      // channel chunks must be whole for the fixed-size transaction counts: C % 64 == 0 (NCHW groups of 8 / NHWC box)
+      if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && C % kCChunk == 0) {
+        const int HP = (Hf + 3) & ~3, npix = Hf * 4;
+        const int gstride = ((8 * npix + 31) & ~31) + 4;
+        const int feat_floats = feat_layout ? npix * kCChunk : 8 * gstride;
+        const size_t smem_tma = 128 + ((size_t)((D * npix + 31) & ~31) + ((feat_floats + 31) & ~31) + 2 * (size_t)D * 4 * HP +
+                                       (size_t)D * 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
+        if (smem_tma <= 113 * 1024) {
+          STP3_CUDA_OK(cudaFuncSetAttribute(lift_splat_scatter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem_tma));
+          lift_splat_scatter_tma_kernel<<<(unsigned)nblk, kScatterThreads, smem_tma, stream>>>(maps, p);
+          STP3_CUDA_OK(cudaGetLastError());
+          used_tma = true;
+        }
+      }
+    }
+  }
+  if (!used_tma)
+    rc = TW == 4 ? launch(lift_splat_scatter_kernel<4>)
+       : TW == 2 ? launch(lift_splat_scatter_kernel<2>) : launch(lift_splat_scatter_kernel<1>);
   if (rc != STP3_OK) return rc;
 
   const int nvox = nx * ny * nz;
