@@ -343,8 +343,10 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 // (cp.async.bulk.tensor, 3-D boxes) the moment the CTA starts, and the pure-ALU rank computation (phase B) runs while
 // they are in flight; nothing in the kernel waits on a global load except the two mbarrier waits.
 //   logits   box (4 w, Hf, D)      -> s_stage [D][Hf][4]            (softmax transposes it into s_prob [D][4][HP])
-//   features NCHW: 8 boxes (4 w, Hf, 8 ch) -> s_feat[g][8][Hf][4] with a group stride == 4 (mod 32) floats
-//            NHWC: 1 box (64 ch, 4 w, Hf)  -> s_feat[Hf][4][64]
+//   features NHWC: 1 box (64 ch, 4 w, Hf)  -> s_feat[Hf][4][64]   (channel pairs are float2-readable, conflict free)
+//            NCHW: TMA destinations are 128-byte granular, which would force a 16-way bank conflict on the register
+//                  fill; the tile is fetched with 4-byte cp.async (LDGSTS) straight into the permuted / odd-stride
+//                  rows of lift_splat_scatter_kernel instead -- equally asynchronous, no registers involved
 constexpr int kTmaTW = 4;
 
 struct LiftSplatTmaMaps {
@@ -352,8 +354,11 @@ struct LiftSplatTmaMaps {
   CUtensorMap feat;    // NCHW: (Wf, Hf, C * n_img) fp32 ; NHWC: (C, Wf, Hf * n_img) fp32
 };
 
-__device__ __forceinline__ int feat_index_nchw(int cl, int h, int wl, int Hf, int gstride) {
-  return (cl >> 3) * gstride + (cl & 7) * Hf * kTmaTW + h * kTmaTW + wl;
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kScatterThreads, 2)
@@ -364,8 +369,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C;
   const int HP = (Hf + 3) & ~3;
   const int npix = Hf * TW;
-  const int gstride = ((8 * npix + 31) & ~31) + 4;                 // floats between 8-channel groups (== 4 mod 32)
-  const int feat_floats = p.feat_nhwc ? npix * kCChunk : 8 * gstride;
+  const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * TW) | 1;   // NCHW rows: odd, zero-padded to whole h-chunks
+  const int feat_floats = p.feat_nhwc ? npix * kCChunk : kCChunk * fstride;
   float* s_stage = reinterpret_cast<float*>(smem_raw);             // [D][Hf][TW] raw logits (TMA destination)
   float* s_feat = s_stage + ((D * npix + 31) & ~31);               // feature tile (TMA destination)
   float* s_prob = s_feat + ((feat_floats + 31) & ~31);             // [D][TW][HP]
@@ -395,28 +400,41 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
     ptx::fence_mbar_init();
   }
   __syncthreads();
-  auto issue_features = [&](int c0) {     // one thread: arm the barrier and start the feature tile of channels [c0, c0+64)
-    if (p.feat_nhwc) {
-      ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(npix * kCChunk * 4));
-      ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], c0, w0, img * Hf);
-    } else {
-      ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(kCChunk * npix * 4));
-      for (int g = 0; g < 8; ++g)
-        ptx::tma_load_3d(s_feat + g * gstride, &maps.feat, &bars[1], w0, 0, img * C + c0 + 8 * g);
-    }
-  };
-  if (tid == 0) {
-    if (p.use_depth) {
-      ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)(D * npix * 4));
-      ptx::tma_load_3d(s_stage, &maps.depth, &bars[0], w0, 0, img * D);
-    }
-    issue_features(0);
-  }
-
   const int npix_r = (npix + 31) & ~31;
   const int parts = max(1, nthr / npix_r);
   const int my_part = (nthr / npix_r) <= 1 ? 0 : tid / npix_r;
   const int dchunk = (D + parts - 1) / parts;
+
+  // start the feature tile of channels [c0, c0+64): NHWC = one TMA box (thread 0), NCHW = 4-byte cp.async by all
+  auto issue_features = [&](int c0) {
+    if (p.feat_nhwc) {
+      if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(npix * kCChunk * 4));
+        ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], c0, w0, img * Hf);
+      }
+    } else {
+      for (int px0 = 0; px0 < npix; px0 += npix_r) {
+        const int px = px0 + tid % npix_r;
+        if (px < npix && my_part < parts) {
+          const int wl = px % TW, h = px / TW;
+          const int w = w0 + wl;
+          if (w < Wf) {
+            const float* src = p.feat + (((size_t)img * C + c0) * Hf + h) * Wf + w;
+            for (int cl = my_part; cl < kCChunk; cl += parts)
+              cp_async_4(s_feat + feat_row(cl) * fstride + px, src + (size_t)cl * Hf * Wf);
+          }
+        }
+      }
+    }
+  };
+  if (!p.feat_nhwc)                                       // zero padding / out-of-image columns of the NCHW rows
+    for (int i = tid; i < kCChunk * fstride; i += nthr) s_feat[i] = 0.f;
+  if (tid == 0 && p.use_depth) {
+    ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)(D * npix * 4));
+    ptx::tma_load_3d(s_stage, &maps.depth, &bars[0], w0, 0, img * D);
+  }
+  __syncthreads();                                        // zero fill complete before the async copies land
+  issue_features(0);
 
   if (tid < 9) s_mat[tid] = p.cam_M[img * 9 + tid];
   if (tid >= 9 && tid < 12) s_mat[tid] = p.cam_t[img * 3 + tid - 9];
@@ -537,8 +555,13 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   const bool vec_ok = (C % 2) == 0;
   uint32_t fphase = 0;
   for (int c0 = 0; c0 < C; c0 += kCChunk) {
-    ptx::mbar_wait(&bars[1], fphase);
-    fphase ^= 1;
+    if (p.feat_nhwc) {
+      ptx::mbar_wait(&bars[1], fphase);
+      fphase ^= 1;
+    } else {
+      cp_async_commit_wait_all();
+      __syncthreads();
+    }
     const int c = c0 + 2 * lane;
     const bool mark = (lane == 0) && (c0 == 0);
     for (int item = warp; item < TW * dsplit; item += nwarps) {
@@ -557,8 +580,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
               const float2 v = *reinterpret_cast<const float2*>(s_feat + (h * TW + wl) * kCChunk + 2 * lane);
               f0[j] = v.x; f1[j] = v.y;
             } else {
-              f0[j] = s_feat[feat_index_nchw(2 * lane, h, wl, Hf, gstride)];
-              f1[j] = s_feat[feat_index_nchw(2 * lane + 1, h, wl, Hf, gstride)];
+              f0[j] = s_feat[lane * fstride + h * TW + wl];
+              f1[j] = s_feat[(lane + 32) * fstride + h * TW + wl];
             }
           }
         }
@@ -603,7 +626,7 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
     }
     if (c0 + kCChunk < C) {              // next 64 channels: the tile buffer is free once every warp is done with it
       __syncthreads();
-      if (tid == 0) issue_features(c0 + kCChunk);
+      issue_features(c0 + kCChunk);
     }
   }
 }
@@ -897,13 +920,8 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
         memset(&maps.depth, 0, sizeof(maps.depth));
       }
       if (feat_layout == 0) {
-        const cuuint64_t dims[3] = {(cuuint64_t)Wf, (cuuint64_t)Hf, (cuuint64_t)(C * n_img)};
-        const cuuint64_t strides[2] = {(cuuint64_t)Wf * 4, (cuuint64_t)Hf * Wf * 4};
-        const cuuint32_t box[3] = {4, (cuuint32_t)Hf, 8};
-        const cuuint32_t es[3] = {1, 1, 1};
-        r2 = enc(&maps.feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dims, strides, box, es,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        memset(&maps.feat, 0, sizeof(maps.feat));       // NCHW features travel by cp.async, no tensor map
+        r2 = CUDA_SUCCESS;
       } else {
         const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Wf, (cuuint64_t)(Hf * n_img)};
         const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)Wf * C * 4};
@@ -916,8 +934,8 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
       // channel chunks must be whole for the fixed-size transaction counts: C % 64 == 0 (NCHW groups of 8 / NHWC box)
       if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && C % kCChunk == 0) {
         const int HP = (Hf + 3) & ~3, npix = Hf * 4;
-        const int gstride = ((8 * npix + 31) & ~31) + 4;
-        const int feat_floats = feat_layout ? npix * kCChunk : 8 * gstride;
+        const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * 4) | 1;
+        const int feat_floats = feat_layout ? npix * kCChunk : kCChunk * fstride;
         const size_t smem_tma = 128 + ((size_t)((D * npix + 31) & ~31) + ((feat_floats + 31) & ~31) + 2 * (size_t)D * 4 * HP +
                                        (size_t)D * 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
         if (smem_tma <= 113 * 1024) {
