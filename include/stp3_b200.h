@@ -178,6 +178,25 @@ int stp3_upsample2x_add(const void* x_hi, const void* x_lo, int n_img, int h, in
                         const void* s_lo, int s_cstride, int s_coff, void* y_hi, void* y_lo, int y_cstride, int y_coff,
                         int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Frame-sharded lift-splat (latency mode): when the global batch is smaller than the number of GPUs the
+ * B*S camera frames are split across ranks.  Each rank splats its flat frames f_begin + [0, f_count) (f = b*S + t, the
+ * ego-motion chain of frame t still uses the poses t..S-2 of its sample) and writes them RAW -- no discount
+ * recurrence -- as channels-last fp32 grids out_raw (f_count, nx, ny, C).  After ONE all-gather of those grids
+ * (ncclAllGather over NVLink; stp3_b200/parallel.py) every rank holds (B, S, nx, ny, C) and stp3_bev_discount applies
+ * out[t] = out[t-1]*discount + raw[t] (stp3.py:296) and emits the bf16 hi/lo planes the temporal block consumes.
+ * workspace: stp3_lift_splat_workspace_bytes(f_count, 1, C, nx, ny) bytes, all-zero on entry (same invariant). */
+int stp3_lift_splat_frames_fwd(const float* feat, int feat_layout, const float* depth_logits,
+                               const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                               const float* xs, const float* ys, const float* ds,
+                               const float* bev_off /*host[3]*/, const float* bev_res /*host[3]*/,
+                               int nx, int ny, int nz,
+                               int B, int S, int N, int D, int Hf, int Wf, int C,
+                               int use_depth_distribution, int f_begin, int f_count,
+                               void* workspace, size_t workspace_bytes, float* out_raw, void* stream);
+int stp3_bev_discount(const float* raw /*(B,S,nx,ny,C) fp32*/, int B, int S, int nx, int ny, int C, float discount,
+                      void* out_hi, void* out_lo /*(B,S,nx,ny,C) bf16 each*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,7 @@ struct LiftSplatParams {
   int B, S, N, D, Hf, Wf, C;
   int feat_nhwc;
   int use_depth;
+  int f_begin;   // first flat frame (b*S + t) processed by this launch; CTAs enumerate f_begin + [0, f_count)
   int TW;        // image columns per CTA
   int tiles_w;   // ceil(Wf / TW)
   int32_t* ranks_out;
@@ -118,11 +119,12 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
   int blk = blockIdx.x;
   const int tile = blk % p.tiles_w; blk /= p.tiles_w;
   const int n = blk % p.N; blk /= p.N;
-  const int t = blk % p.S;
-  const int b = blk / p.S;
+  const int frame = p.f_begin + blk;             // flat frame index b*S + t
+  const int t = frame % p.S;
+  const int b = frame / p.S;
   const int w0 = tile * TW;
-  const int img = (b * p.S + t) * p.N + n;       // camera-image index
-  const int bt = b * p.S + t;
+  const int img = frame * p.N + n;               // camera-image index
+  const int bt = blk;                            // slot of this frame in the scatter grid of this launch
   const int n_chain = p.S - 1 - t;               // poses t .. S-2 applied in order (stp3.py:270-277)
 
   // thread <-> pixel mapping shared by phases A and B: `parts` threads per pixel, each owning a slice of D
@@ -387,11 +389,12 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   int blk = blockIdx.x;
   const int tile = blk % p.tiles_w; blk /= p.tiles_w;
   const int n = blk % p.N; blk /= p.N;
-  const int t = blk % p.S;
-  const int b = blk / p.S;
+  const int frame = p.f_begin + blk;
+  const int t = frame % p.S;
+  const int b = frame / p.S;
   const int w0 = tile * TW;
-  const int img = (b * p.S + t) * p.N + n;
-  const int bt = b * p.S + t;
+  const int img = frame * p.N + n;
+  const int bt = blk;
   const int n_chain = p.S - 1 - t;
 
   if (tid == 0) {
@@ -831,17 +834,23 @@ extern "C" int stp3_lift_splat_workspace_init(void* workspace, size_t workspace_
   return STP3_OK;
 }
 
-extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_logits,
-                                   const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
-                                   const float* xs, const float* ys, const float* ds,
-                                   const float* bev_off, const float* bev_res,
-                                   int nx, int ny, int nz, float discount,
-                                   int B, int S, int N, int D, int Hf, int Wf, int C,
-                                   int use_depth_distribution,
-                                   int32_t* ranks_out, float* pool_sum,
-                                   void* workspace, size_t workspace_bytes,
-                                   float* out, int out_layout, void* stream_) {
+// Shared implementation.  f_count < 0: the normal call (all B*S frames, discount recurrence over each sample's S
+// frames).  f_count >= 0: frame-sharded call -- only the flat frames f_begin + [0, f_count) are splatted and written
+// RAW (no recurrence), one (nx, ny, C) grid per frame; the caller all-gathers them and applies stp3_bev_discount.
+static int lift_splat_impl(const float* feat, int feat_layout, const float* depth_logits,
+                           const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                           const float* xs, const float* ys, const float* ds,
+                           const float* bev_off, const float* bev_res,
+                           int nx, int ny, int nz, float discount,
+                           int B, int S, int N, int D, int Hf, int Wf, int C,
+                           int use_depth_distribution,
+                           int32_t* ranks_out, float* pool_sum,
+                           void* workspace, size_t workspace_bytes,
+                           float* out, int out_layout, int f_begin, int f_count, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool raw = f_count >= 0;
+  if (raw) STP3_CHECK_ARG(f_begin >= 0 && f_count > 0 && f_begin + f_count <= B * S, "frame range outside [0, B*S)");
+  const int Bw = raw ? f_count : B, Sw = raw ? 1 : S;      // shape of the scatter grid / finalize launch
   STP3_CHECK_ARG(feat && cam_M && cam_t && ego_R && ego_t && xs && ys && ds && bev_off && bev_res && out && workspace,
                  "stp3_lift_splat_fwd: null pointer argument");
   STP3_CHECK_ARG(use_depth_distribution == 0 || depth_logits, "depth_logits is NULL but use_depth_distribution=1");
@@ -854,10 +863,11 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   STP3_CHECK_ARG(out_layout >= 0 && out_layout <= 2, "out_layout must be 0 (C,X,Y), 1 (X,Y,C) or 2 (bf16 hi/lo X,Y,C)");
   STP3_CHECK_ARG(out_layout != 2 || C % 8 == 0, "out_layout 2 needs C %% 8 == 0");
   STP3_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  const size_t need = stp3_lift_splat_workspace_bytes(B, S, C, nx, ny);
+  const size_t need = stp3_lift_splat_workspace_bytes(Bw, Sw, C, nx, ny);
   if (workspace_bytes < need) return set_error(STP3_ENOSPC, "workspace too small: %zu < %zu", workspace_bytes, need);
 
   LiftSplatParams p;
+  p.f_begin = raw ? f_begin : 0;
   p.feat = feat; p.depth = depth_logits; p.cam_M = cam_M; p.cam_t = cam_t; p.ego_R = ego_R; p.ego_t = ego_t;
   p.xs = xs; p.ys = ys; p.ds = ds;
   for (int i = 0; i < 3; ++i) {
@@ -872,7 +882,7 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   p.feat_nhwc = feat_layout; p.use_depth = use_depth_distribution;
   p.ranks_out = ranks_out;
   p.grid = static_cast<float*>(workspace);
-  p.occ = static_cast<unsigned char*>(workspace) + grid_bytes(B, S, C, nx, ny);
+  p.occ = static_cast<unsigned char*>(workspace) + grid_bytes(Bw, Sw, C, nx, ny);
 
   // tile width: as wide as shared memory allows (<= 4 columns), at least 1
   int TW = 4;
@@ -887,7 +897,7 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
   STP3_CHECK_ARG(smem <= 227 * 1024, "D*Hf = %d too large for one image column in shared memory", D * Hf);
   p.TW = TW;
   p.tiles_w = ceil_div(Wf, TW);
-  const long long nblk = (long long)B * S * N * p.tiles_w;
+  const long long nblk = (long long)Bw * Sw * N * p.tiles_w;
   STP3_CHECK_ARG(nblk < (1ll << 31), "grid too large");
   auto launch = [&](auto kernel) -> int {
     STP3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -955,23 +965,95 @@ extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const flo
 
   const int nvox = nx * ny * nz;
   const int groups = ceil_div(C, 64);                 // 8 warps x 8 channels per CTA
-  dim3 fgrid(ceil_div(nvox, 32), B, groups), fblock(32, C >= 64 ? 8 : ceil_div(C, 8));
-  float* pool_part = pool_sum ? reinterpret_cast<float*>(p.occ + occ_bytes(B, S, nx, ny)) : nullptr;
+  dim3 fgrid(ceil_div(nvox, 32), Bw, groups), fblock(32, C >= 64 ? 8 : ceil_div(C, 8));
+  float* pool_part = pool_sum ? reinterpret_cast<float*>(p.occ + occ_bytes(Bw, Sw, nx, ny)) : nullptr;
 #define STP3_FINALIZE(VEC, SMAX) \
-  bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_part, S, C, nvox, discount, out_layout)
-  if (C % 8 == 0) { if (S <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
-  else            { if (S <= 4) STP3_FINALIZE(false, 4); else STP3_FINALIZE(false, 8); }
+  bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, C, nvox, discount, out_layout)
+  if (C % 8 == 0) { if (Sw <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
+  else            { if (Sw <= 4) STP3_FINALIZE(false, 4); else STP3_FINALIZE(false, 8); }
 #undef STP3_FINALIZE
   STP3_CUDA_OK(cudaGetLastError());
   if (pool_sum) {
-    STP3_CUDA_OK(cudaMemsetAsync(pool_sum, 0, (size_t)B * S * C * sizeof(float), stream));
-    pool_reduce_kernel<<<dim3(B * S, kPoolSlices), dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), S, C, pool_sum);
+    STP3_CUDA_OK(cudaMemsetAsync(pool_sum, 0, (size_t)Bw * Sw * C * sizeof(float), stream));
+    pool_reduce_kernel<<<dim3(Bw * Sw, kPoolSlices), dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), Sw, C, pool_sum);
     STP3_CUDA_OK(cudaGetLastError());
   }
   if (groups > 1) {
-    const size_t nocc = ((size_t)B * S * nvox + 255) & ~(size_t)255;
+    const size_t nocc = ((size_t)Bw * Sw * nvox + 255) & ~(size_t)255;
     clear_bytes_kernel<<<(unsigned)((nocc / 16 + 255) / 256), 256, 0, stream>>>(p.occ, nocc);
     STP3_CUDA_OK(cudaGetLastError());
   }
+  return STP3_OK;
+}
+
+
+extern "C" int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_logits,
+                                   const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                                   const float* xs, const float* ys, const float* ds,
+                                   const float* bev_off, const float* bev_res,
+                                   int nx, int ny, int nz, float discount,
+                                   int B, int S, int N, int D, int Hf, int Wf, int C,
+                                   int use_depth_distribution,
+                                   int32_t* ranks_out, float* pool_sum,
+                                   void* workspace, size_t workspace_bytes,
+                                   float* out, int out_layout, void* stream) {
+  return lift_splat_impl(feat, feat_layout, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, nx, ny,
+                         nz, discount, B, S, N, D, Hf, Wf, C, use_depth_distribution, ranks_out, pool_sum, workspace,
+                         workspace_bytes, out, out_layout, 0, -1, stream);
+}
+
+extern "C" int stp3_lift_splat_frames_fwd(const float* feat, int feat_layout, const float* depth_logits,
+                                          const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                                          const float* xs, const float* ys, const float* ds,
+                                          const float* bev_off, const float* bev_res,
+                                          int nx, int ny, int nz,
+                                          int B, int S, int N, int D, int Hf, int Wf, int C,
+                                          int use_depth_distribution, int f_begin, int f_count,
+                                          void* workspace, size_t workspace_bytes, float* out_raw, void* stream) {
+  STP3_CHECK_ARG(f_count > 0, "stp3_lift_splat_frames_fwd: empty frame range");
+  return lift_splat_impl(feat, feat_layout, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, nx, ny,
+                         nz, 0.f, B, S, N, D, Hf, Wf, C, use_depth_distribution, nullptr, nullptr, workspace,
+                         workspace_bytes, out_raw, 1, f_begin, f_count, stream);
+}
+
+namespace stp3 {
+// out[b,t] = out[b,t-1]*discount + raw[b,t] over channels-last fp32 raw splats, written as bf16 hi/lo planes
+// (the discount recurrence of stp3.py:296 applied after the frames were all-gathered); one thread = 8 channels of a cell
+__global__ void __launch_bounds__(256)
+bev_discount_kernel(const float* __restrict__ raw, int S, size_t cells8, float discount, __nv_bfloat16* __restrict__ hi,
+                    __nv_bfloat16* __restrict__ lo, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t b = idx / cells8, r = idx % cells8;       // r = (cell, 8-channel group) within one frame
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < S; ++t) {
+    const size_t off = ((b * S + t) * cells8 + r) * 8;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(raw + off));
+    const float4 c = __ldcs(reinterpret_cast<const float4*>(raw + off) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] = __fadd_rn(__fmul_rn(acc[2 * e], discount), v[2 * e]);
+      acc[2 * e + 1] = __fadd_rn(__fmul_rn(acc[2 * e + 1], discount), v[2 * e + 1]);
+      const uint32_t h = ptx::pack_bf16x2(acc[2 * e], acc[2 * e + 1]);
+      hw[e] = h;
+      lw[e] = ptx::pack_bf16x2(acc[2 * e] - __uint_as_float(h << 16), acc[2 * e + 1] - __uint_as_float(h & 0xFFFF0000u));
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+}  // namespace stp3
+
+extern "C" int stp3_bev_discount(const float* raw, int B, int S, int nx, int ny, int C, float discount, void* out_hi,
+                                 void* out_lo, void* stream) {
+  STP3_CHECK_ARG(raw && out_hi && out_lo && B > 0 && S > 0 && nx > 0 && ny > 0 && C > 0 && C % 8 == 0,
+                 "stp3_bev_discount: bad argument (C must be a multiple of 8)");
+  const size_t cells8 = (size_t)nx * ny * (C / 8);
+  const size_t total = (size_t)B * cells8;
+  bev_discount_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      raw, S, cells8, discount, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), total);
+  STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }

@@ -173,6 +173,41 @@ class STP3(nn.Module):
         self._mark("decoder")
         return output
 
+    def forward_features_frame_sharded(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        """Latency mode for a global batch smaller than the number of GPUs: the B*S camera frames are
+        split across the ranks of the default process group, every rank splats only its frames, ONE all-gather of
+        the raw BEV grids follows, and the (cheap, elementwise) discount recurrence, the temporal model and the
+        decoder run replicated.  Every rank passes the same full inputs and returns the same outputs."""
+        from .. import parallel
+        S = self.receptive_field
+        dev = feat.device
+        h = {k: v.to(dev) for k, v in self.prepare_inputs(intrinsics, extrinsics, future_egomotion).items()}
+        feat = feat[:, :S].contiguous()
+        depth_logits = depth_logits[:, :S].contiguous() if depth_logits is not None else None
+        B = feat.shape[0]
+        X, Y = self.bev_size
+        C = self.encoder_out_channels
+        off, res, dim = self._bev_host()
+        rank, world = parallel.world()
+        f0, fc = parallel.shard_batch(B * S, rank, world)
+        if fc > 0:
+            raw = ops.lift_splat_frames(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(),
+                                        off, res, dim, f0, fc,
+                                        use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
+                                        workspace=self._ws)
+        else:
+            raw = torch.empty((0, X, Y, C), dtype=torch.float32, device=dev)
+        raw = parallel.all_gather_frames(raw, B * S).view(B, S, X, Y, C)
+        planes = ops.bev_discount(raw, float(self.discount))
+        x = dense.HL(planes[0], planes[1], C)
+        output = {'depth_prediction': depth_logits, 'cam_front': None}
+        use_ego = self.cfg.MODEL.TEMPORAL_MODEL.INPUT_EGOPOSE
+        if isinstance(self.temporal_model, TemporalModelIdentity):
+            raise NotImplementedError("frame-sharded mode is wired for the temporal_block model")
+        states = self.temporal_model.forward_hl(x, const=h["const"] if use_ego else None, sums=None)
+        output.update(self.decoder.forward_hl(states))
+        return output
+
     def _mark(self, name):
         if self.stage_events is not None:
             ev = torch.cuda.Event(enable_timing=True)

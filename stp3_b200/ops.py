@@ -108,3 +108,51 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
     if pool_sum:
         res += (psum,)
     return res if len(res) > 1 else out
+
+
+def lift_splat_frames(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
+                      f_begin: int, f_count: int, *, feat_channels_last: bool = False,
+                      use_depth_distribution: bool = True, workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """Frame-sharded lift-splat: RAW (no discount recurrence) channels-last splats (f_count, X, Y, C) fp32 of the flat
+    frames f_begin + [0, f_count), f = b*S + t.  See stp3_lift_splat_frames_fwd in include/stp3_b200.h."""
+    _require_cuda(feat, depth_logits)
+    dev = feat.device
+    if feat_channels_last:
+        B, S, N, Hf, Wf, C = feat.shape
+    else:
+        B, S, N, C, Hf, Wf = feat.shape
+    D = ds.numel()
+    nx, ny, nz = (int(v) for v in bev_dim)
+    feat = _f32c(feat)
+    depth_logits = _f32c(depth_logits) if depth_logits is not None else None
+    cam_M, cam_t, ego_R, ego_t = (_f32c(t.to(dev)) for t in (cam_M, cam_t, ego_R, ego_t))
+    xs, ys, ds = (_f32c(t.to(dev)) for t in (xs, ys, ds))
+    L = _lib.lib()
+    need = L.stp3_lift_splat_workspace_bytes(f_count, 1, C, nx, ny)
+    ws = (workspace or _default_ws).get(need, dev)
+    out = torch.empty((f_count, nx, ny, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        code = L.stp3_lift_splat_frames_fwd(
+            feat.data_ptr(), int(feat_channels_last), depth_logits.data_ptr() if depth_logits is not None else None,
+            cam_M.data_ptr(), cam_t.data_ptr(), ego_R.data_ptr(), ego_t.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+            ds.data_ptr(), _host3(bev_off), _host3(bev_res), nx, ny, nz, B, S, N, D, Hf, Wf, C,
+            int(use_depth_distribution), int(f_begin), int(f_count), ws.data_ptr(), ws.numel(), out.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream)
+    if code != 0:
+        (workspace or _default_ws).reset()
+    _lib.check(code, "stp3_lift_splat_frames_fwd")
+    return out
+
+
+def bev_discount(raw: torch.Tensor, discount: float) -> torch.Tensor:
+    """raw (B,S,X,Y,C) fp32 channels-last per-frame splats -> (2,B,S,X,Y,C) bf16 hi/lo planes of
+    out[t] = out[t-1]*discount + raw[t]  (stp3.py:296)."""
+    _require_cuda(raw)
+    raw = _f32c(raw)
+    B, S, X, Y, C = raw.shape
+    planes = torch.empty((2, B, S, X, Y, C), dtype=torch.bfloat16, device=raw.device)
+    with torch.cuda.device(raw.device):
+        code = _lib.lib().stp3_bev_discount(raw.data_ptr(), B, S, X, Y, C, float(discount), planes[0].data_ptr(),
+                                            planes[1].data_ptr(), torch.cuda.current_stream(raw.device).cuda_stream)
+    _lib.check(code, "stp3_bev_discount")
+    return planes

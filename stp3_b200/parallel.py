@@ -60,3 +60,20 @@ def gather_outputs(outputs: Dict[str, Optional[torch.Tensor]], global_batch: int
         dist.all_gather(parts, tp.contiguous())
         out[key] = torch.cat([p[:c] for p, c in zip(parts, counts)])
     return out
+
+
+def all_gather_frames(local: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """The ONE collective of the frame-sharded mode: local (f_count, X, Y, C) raw BEV frames of this rank ->
+    (n_frames, X, Y, C) on every rank, in flat-frame order (rank r owns shard_batch(n_frames, r, world))."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    counts = [shard_batch(n_frames, r, ws)[1] for r in range(ws)]
+    cmax = max(counts)
+    pad = cmax - local.shape[0]
+    lp = torch.cat([local, local.new_zeros((pad, *local.shape[1:]))]) if pad else local.contiguous()
+    gathered = torch.empty((ws * cmax, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, lp)
+    if all(c == cmax for c in counts):
+        return gathered
+    return torch.cat([gathered[r * cmax:r * cmax + c] for r, c in enumerate(counts)])

@@ -56,3 +56,32 @@ def test_shard_batch_properties():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
     with pytest.raises(ValueError):
         parallel.shard_batch(4, 2, 2)
+
+
+def _gather_worker(rank, world_size, port, n_frames, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        f0, fc = parallel.shard_batch(n_frames, rank, world_size)
+        local = torch.arange(f0, f0 + fc, dtype=torch.float32).view(fc, 1, 1, 1).expand(fc, 2, 2, 3).contiguous()
+        allf = parallel.all_gather_frames(local, n_frames)
+        q.put((rank, allf[:, 0, 0, 0].tolist(), tuple(allf.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [3, 6])
+def test_all_gather_frames_uneven_and_even(n_frames):
+    """Frame-sharded mode: flat frames b*S+t split over 2 ranks (3 frames -> 2 + 1) and gathered back in order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, 29620 + n_frames, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, order, shape in res:
+        assert order == [float(i) for i in range(n_frames)] and shape == (n_frames, 2, 2, 3)

@@ -140,3 +140,47 @@ def test_pipelined_front_end_matches_eager():
                                            inp["extrinsics"], inp["future_egomotion"])
             for key in ("segmentation", "pedestrian", "hdmap"):
                 assert (out[key] - eager[key].cpu()).abs().max() <= 1e-4 * eager[key].abs().max(), key
+
+
+def _sharded_worker(rank, world_size, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=dev)
+    try:
+        cfg = small_cfg()
+        lcfg = syn.LiftSplatConfig(x_bound=(-8.0, 8.0, 0.5), y_bound=(-8.0, 8.0, 0.5), d_bound=(2.0, 10.0, 1.0),
+                                   final_dim=(32, 48), out_channels=64, n_cameras=2, receptive_field=3)
+        with torch.no_grad():
+            model = syn.init_exact(STP3(cfg, backbone=FakeTrunk()), seed=8).eval()
+            model.frustum.copy_(model.create_frustum())
+            res, start, dim = G.calculate_birds_eye_view_parameters(cfg.LIFT.X_BOUND, cfg.LIFT.Y_BOUND, cfg.LIFT.Z_BOUND)
+            model.bev_resolution.copy_(res); model.bev_start_position.copy_(start); model.bev_dimension.copy_(dim)
+            model = model.to(dev)
+            inp = syn.lift_inputs(lcfg, 1, seed=3, random_pose=True)        # global batch 1 < 2 GPUs
+            a = (inp["feat"].to(dev), inp["depth_logits"].to(dev), inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+            sharded = model.forward_features_frame_sharded(*a)
+            full = model.forward_features(*a)
+            err = max(float((sharded[k] - full[k]).abs().max() / full[k].abs().max()) for k in ("segmentation", "pedestrian", "hdmap"))
+        q.put((rank, err))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharded_forward_two_gpus_nccl():
+    """North-star multi-GPU mode: batch 1 split by camera frame over 2 GPUs, one NCCL all-gather of raw BEV frames."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, 29641, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(err <= 1e-4 for _, err in res), res
