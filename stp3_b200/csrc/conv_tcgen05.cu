@@ -76,9 +76,10 @@ struct ConvParams {
   int head_sigmoid_mask;    // bit k: sigmoid on output k
 };
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct ConvSmem {
-  static constexpr int kBTileBytes = 2 * BN * kBK * 2;                 // B_hi + B_lo of one K step
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;                    // weight rows held by one CTA (a pair splits N)
+  static constexpr int kBTileBytes = 2 * kBRows * kBK * 2;             // B_hi + B_lo of one K step
   static constexpr int kTmemCols = 4 * BN;                             // 2 sub-tiles x 2 accumulator buffers
   static constexpr size_t tail_bytes() {
     return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) +
@@ -94,11 +95,23 @@ struct ConvSmem {
 //     offsets 0, 16, 32 (2 KB steps keep the 1024-byte swizzle alignment), so A traffic drops 2.4x.
 //   * The MMA thread alternates between two TMEM accumulator buffers; eight epilogue warps drain one while the tensor
 //     pipe fills the other.
-template <int BN>
+//
+// PAIR = true: two CTAs of a cluster (one TPC) share a 16x16 tile through tcgen05.mma.cta_group::2 (UMMA M = 256): each
+// CTA stages its own 8 image rows of A and HALF of the weight rows, the leader (cluster rank 0) issues every MMA, both
+// tensor cores read both weight halves, and each CTA's epilogue drains its own 128 accumulator rows.  Shared-memory
+// operand reads per MMA drop by a quarter and the weight traffic per SM halves.  Barrier protocol: "full" barriers
+// live in the leader and collect the TMA bytes of both CTAs; "empty" / "accumulator ready" are multicast commits;
+// "accumulator drained" collects the epilogue warps of both CTAs in the leader.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
-  using S = ConvSmem<BN>;
+  using S = ConvSmem<BN, PAIR>;
+  constexpr int kBRows = S::kBRows;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;              // 0 = leader
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a pair walks together)
+  const int n_cta = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr uint32_t kProd = PAIR ? 2 : 1;                               // producers arriving on a "full" barrier
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle; plain offset arithmetic keeps the pointer in the shared state space
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -124,38 +137,58 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
-    for (int i = 0; i < p.na_stages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.nb_stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
-    ptx::mbar_init(bres_bar, 1);
+    for (int i = 0; i < p.na_stages; ++i) { ptx::mbar_init(&a_full[i], kProd); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.nb_stages; ++i) { ptx::mbar_init(&b_full[i], kProd); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps * kProd);
+    }
+    ptx::mbar_init(bres_bar, kProd);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) ptx::tmem_alloc_pair<S::kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+  }
   for (int i = threadIdx.x; i < BN; i += blockDim.x) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < p.head_ko * BN; i += blockDim.x) s_head[i] = p.head_w[i];
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();        // the peer's barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_groups = p.ntaps / p.group;
+  const int tile_h = PAIR ? 2 * kSubH : kSubH * p.n_sub;      // image rows of a tile (a pair: 8 per CTA)
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loops; one elected lane issues) =====================
     {
+      // in a pair every "full" barrier is the leader's: arrive / complete_tx go through its shared::cluster address
+      const int w_row0 = p.w_row_off + (int)rank * kBRows;
       if (resident && ptx::elect_one_sync()) {
-        ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
-        for (int it = 0; it < k_iters; ++it) {
-          unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
-          ptx::tma_load_2d(dst, &tm_w, bres_bar, 0, (it * 2) * p.w_rows + p.w_row_off);
-          ptx::tma_load_2d(dst + BN * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
+        if constexpr (PAIR) {
+          const uint32_t bar = ptx::mapa(ptx::smem_u32(bres_bar), 0);
+          ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)(k_iters * S::kBTileBytes));
+          for (int it = 0; it < k_iters; ++it) {
+            unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
+            ptx::tma_load_2d_pair(dst, &tm_w, bar, 0, (it * 2) * p.w_rows + w_row0);
+            ptx::tma_load_2d_pair(dst + kBRows * kBK * 2, &tm_w, bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
+          }
+        } else {
+          ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
+          for (int it = 0; it < k_iters; ++it) {
+            unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
+            ptx::tma_load_2d(dst, &tm_w, bres_bar, 0, (it * 2) * p.w_rows + w_row0);
+            ptx::tma_load_2d(dst + kBRows * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
+          }
         }
       }
       __syncwarp();
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
         const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-        const int oy0 = (rem / p.tiles_x) * (kSubH * p.n_sub), ox0 = (rem % p.tiles_x) * kTileW;
+        const int oy0 = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox0 = (rem % p.tiles_x) * kTileW;
         const int bidx = img / p.T, tidx = p.t0 + img % p.T;
         for (int grp = 0; grp < n_groups; ++grp) {
           const int tap0 = grp * p.group;
@@ -166,10 +199,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             ptx::mbar_wait(&a_empty[as], aph ^ 1);
             if (ptx::elect_one_sync()) {
               unsigned char* sa = a_ring + (size_t)as * a_stage_bytes;
-              ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
               const int c = p.cin_off + kb * kBK;
-              ptx::tma_load_5d(sa, &tm_a_hi, &a_full[as], c, x, y, t, bidx);
-              ptx::tma_load_5d(sa + p.a_plane_bytes, &tm_a_lo, &a_full[as], c, x, y, t, bidx);
+              if constexpr (PAIR) {
+                const uint32_t bar = ptx::mapa(ptx::smem_u32(&a_full[as]), 0);
+                ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)a_stage_bytes);
+                ptx::tma_load_5d_pair(sa, &tm_a_hi, bar, c, x, y, t, bidx);
+                ptx::tma_load_5d_pair(sa + p.a_plane_bytes, &tm_a_lo, bar, c, x, y, t, bidx);
+              } else {
+                ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)a_stage_bytes);
+                ptx::tma_load_5d(sa, &tm_a_hi, &a_full[as], c, x, y, t, bidx);
+                ptx::tma_load_5d(sa + p.a_plane_bytes, &tm_a_lo, &a_full[as], c, x, y, t, bidx);
+              }
             }
             __syncwarp();
             if (++as == p.na_stages) { as = 0; aph ^= 1; }
@@ -179,9 +219,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 ptx::mbar_wait(&b_empty[bs], bph ^ 1);
                 if (ptx::elect_one_sync()) {
                   unsigned char* sb = b_ring + (size_t)bs * S::kBTileBytes;
-                  ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
-                  ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + p.w_row_off);
-                  ptx::tma_load_2d(sb + BN * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + p.w_row_off);
+                  if constexpr (PAIR) {
+                    const uint32_t bar = ptx::mapa(ptx::smem_u32(&b_full[bs]), 0);
+                    ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)S::kBTileBytes);
+                    ptx::tma_load_2d_pair(sb, &tm_w, bar, 0, (it * 2) * p.w_rows + w_row0);
+                    ptx::tma_load_2d_pair(sb + kBRows * kBK * 2, &tm_w, bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
+                  } else {
+                    ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
+                    ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + w_row0);
+                    ptx::tma_load_2d(sb + kBRows * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + w_row0);
+                  }
                 }
                 __syncwarp();
                 if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
@@ -191,20 +238,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
     {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
-      if (resident) ptx::mbar_wait(bres_bar, 0);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 256 : 128, BN);
+      // plain (CTA-scope) waits also for the barriers the peer signals: the data they guard moves through the async
+      // proxy (TMA -> UMMA) or TMEM (ordered by the tcgen05 fences); a cluster-scope acquire on the MMA-issuing thread
+      // costs ~0.7 us per wait and starves the tensor pipe
+      auto wait_full = [](uint64_t* bar, uint32_t ph) { ptx::mbar_wait(bar, ph); };
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if constexpr (PAIR) ptx::umma_bf16_pair(d, a, b, id, acc); else ptx::umma_bf16(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (PAIR) ptx::umma_commit_pair(bar); else ptx::umma_commit(bar);
+      };
+      if (resident) wait_full(bres_bar, 0);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       int buf = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1);      // the epilogue has drained this accumulator pair
+      for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+        wait_full(&tmem_empty_bar[buf], acc_phase ^ 1);           // the epilogue has drained this accumulator pair
         ptx::tc_fence_after();
         uint32_t accumulate = 0;
         for (int grp = 0; grp < n_groups; ++grp) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            ptx::mbar_wait(&a_full[as], aph);
+            wait_full(&a_full[as], aph);
             ptx::tc_fence_after();
             const uint32_t a_hi0 = ptx::smem_u32(a_ring + (size_t)as * a_stage_bytes);
             for (int j = 0; j < p.group; ++j) {
@@ -213,13 +270,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               if (resident) {
                 b_hi = ptx::smem_u32(b_ring + (size_t)it * S::kBTileBytes);
               } else {
-                ptx::mbar_wait(&b_full[bs], bph);
+                wait_full(&b_full[bs], bph);
                 ptx::tc_fence_after();
                 b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
               }
-              const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + BN * kBK * 2);
+              const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + kBRows * kBK * 2);
               if (ptx::elect_one_sync()) {
-              for (int sub = 0; sub < p.n_sub; ++sub) {
+              for (int sub = 0; sub < (PAIR ? 1 : p.n_sub); ++sub) {
                 // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
                 const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
                 const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_hi + p.a_plane_bytes);
@@ -227,28 +284,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                   const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
-                  ptx::umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
-                  ptx::umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                  ptx::umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                  mma(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
+                  mma(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                  mma(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
                 }
               }
-              if (!resident) ptx::umma_commit(&b_empty[bs]);      // frees the weight slot when these MMAs have read it
+              if (!resident) commit(&b_empty[bs]);                // frees the weight slot when these MMAs have read it
               }
               __syncwarp();
               accumulate = 1;
               if (!resident) { if (++bs == p.nb_stages) { bs = 0; bph ^= 1; } }
             }
-            if (ptx::elect_one_sync()) ptx::umma_commit(&a_empty[as]);          // frees the activation slot
+            if (ptx::elect_one_sync()) commit(&a_empty[as]);                    // frees the activation slot
             __syncwarp();
             if (++as == p.na_stages) { as = 0; aph ^= 1; }
           }
         }
-        if (ptx::elect_one_sync()) ptx::umma_commit(&tmem_full_bar[buf]);       // accumulators complete -> epilogue
+        if (ptx::elect_one_sync()) commit(&tmem_full_bar[buf]);                 // accumulators complete -> epilogue
         __syncwarp();
         if (++buf == 2) { buf = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int e = warp - 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
@@ -257,14 +314,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int col0 = half * kColsPerWarp;
     const int r = q * 32 + lane;                 // row of the sub-tile = output pixel
     int buf = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int oy_t = (rem / p.tiles_x) * (kSubH * p.n_sub), ox = (rem % p.tiles_x) * kTileW + (r & 15);
+      const int oy_t = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
       const float* ib = p.img_bias ? p.img_bias + (size_t)img * p.img_bias_stride : nullptr;
       ptx::mbar_wait(&tmem_full_bar[buf], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < p.n_sub; ++sub) {
+      for (int sub = 0; sub < (PAIR ? 1 : p.n_sub); ++sub) {
         const int oy = oy_t + sub * kSubH + (r >> 4);
         const bool valid = oy < p.Ho && ox < p.Wo;
         const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
@@ -377,13 +434,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       // this warp has finished reading the accumulator pair
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty_bar[buf]), 0));
+        else ptx::mbar_arrive(&tmem_empty_bar[buf]);
+      }
       if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+  if constexpr (PAIR) ptx::cluster_sync();        // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == 1) {
+    if constexpr (PAIR) ptx::tmem_dealloc_pair<S::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -454,9 +518,11 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   // two sub-tiles per tile halve the weight traffic; small images keep one so that there are enough tiles
   const int n_img_ = d->B * d->T;
   const long long tiles16 = (long long)n_img_ * ceil_div(d->Wo, kTileW) * ceil_div(d->Ho, 2 * kSubH);
-  const int n_sub = want_nsub == 1 || want_nsub == 2 ? want_nsub : (tiles16 >= 3 * 148 ? 2 : 1);
-  const int tile_h = kSubH * n_sub;
-  const int box_h = tile_h + (group - 1);
+  // tune_n_sub == 3: the 16x16 tile is shared by a CTA pair (cta_group::2), 8 image rows per CTA
+  const bool pair = want_nsub == 3;
+  const int n_sub = pair ? 1 : (want_nsub == 1 || want_nsub == 2 ? want_nsub : (tiles16 >= 3 * 148 ? 2 : 1));
+  const int tile_h = pair ? 2 * kSubH : kSubH * n_sub;
+  const int box_h = kSubH * n_sub + (group - 1);                         // image rows one CTA loads per stage
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   {
@@ -482,7 +548,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   {
     const cuuint64_t dims[2] = {(cuuint64_t)kBK, (cuuint64_t)d->ntaps * kblocks * 2 * d->bn};
     const cuuint64_t strides[1] = {(cuuint64_t)kBK * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn_launch};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(pair ? bn_launch / 2 : bn_launch)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -519,7 +585,8 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const unsigned grid = (unsigned)(nblk < num_sms ? nblk : num_sms);     // persistent: one CTA per SM
+  unsigned grid = (unsigned)(nblk < num_sms ? nblk : num_sms);           // persistent: one CTA per SM
+  if (pair) grid = 2u * (unsigned)(nblk < num_sms / 2 ? nblk : num_sms / 2);
   const size_t smem_cap = 227 * 1024;
   const size_t a_stage = 2 * (size_t)p.a_plane_bytes;
 
@@ -532,9 +599,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     p.out_coff = d->out_coff + coff;
     p.n_store = n_store - coff < bn_launch ? (n_store - coff > 0 ? n_store - coff : 0) : bn_launch;
     p.f32_coff = coff;
-#define STP3_LAUNCH_CONV(BN_)                                                                                     \
+#define STP3_LAUNCH_CONV(BN_, PAIR_)                                                                              \
     do {                                                                                                          \
-      using SM = ConvSmem<BN_>;                                                                                   \
+      using SM = ConvSmem<BN_, PAIR_>;                                                                            \
       const size_t avail = smem_cap - 1024 - SM::tail_bytes();                                                    \
       const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                    \
       /* small weight tensors stay resident in smem next to >= 2 activation stages */                            \
@@ -556,12 +623,26 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       if (nb > kMaxBStages) nb = kMaxBStages;                                                                     \
       p.na_stages = na; p.nb_stages = nb; p.b_resident = res ? 1 : 0;                                             \
       const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * SM::kBTileBytes) + SM::tail_bytes(); \
-      STP3_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                        (int)smem_cap));                                                          \
-      conv_igemm_kernel<BN_><<<grid, kConvThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_w, p);                   \
+      auto kern = conv_igemm_kernel<BN_, PAIR_>;                                                                  \
+      STP3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));       \
+      cudaLaunchConfig_t cfg = {};                                                                                \
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads);                                                \
+      cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;                                                     \
+      cudaLaunchAttribute attr[1];                                                                                \
+      attr[0].id = cudaLaunchAttributeClusterDimension;                                                           \
+      attr[0].val.clusterDim.x = PAIR_ ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;       \
+      cfg.attrs = attr; cfg.numAttrs = PAIR_ ? 1 : 0;                                                             \
+      if (PAIR_) {                                                                                                \
+        /* co-resident pairs the device can host with this much shared memory (GPCs with an odd SM count) */      \
+        int max_clusters = 0;                                                                                     \
+        STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));                                  \
+        if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");             \
+        if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;             \
+      }                                                                                                           \
+      STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));                                        \
     } while (0)
-    if (bn_launch == 64) STP3_LAUNCH_CONV(64);
-    else STP3_LAUNCH_CONV(128);
+    if (bn_launch == 64) { if (pair) STP3_LAUNCH_CONV(64, true); else STP3_LAUNCH_CONV(64, false); }
+    else { if (pair) STP3_LAUNCH_CONV(128, true); else STP3_LAUNCH_CONV(128, false); }
 #undef STP3_LAUNCH_CONV
     STP3_CUDA_OK(cudaGetLastError());
   }

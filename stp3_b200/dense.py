@@ -125,19 +125,22 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
 
 
 # ------------------------------------------------------------------------------------------------ autotuner
-# The conv kernel has two tiling knobs (sub-tiles per CTA tile, sharing one activation load between the dy taps of a
-# 3x3).  Which combination wins depends on the layer (K depth, N width, image size, whether the weights are
+# The conv kernel has two tiling knobs (sub-tiles per CTA tile -- or a 16x16 tile shared by a CTA pair through
+# tcgen05.mma.cta_group::2, n_sub = 3 -- and sharing one activation load between the dy taps of a 3x3).  Which combination wins depends on the layer (K depth, N width, image size, whether the weights are
 # smem-resident), so the first eager call of every (layer, shape) times the candidates back to back and the winner is
 # cached; CUDA-graph capture then records the tuned launches.  STP3_CONV_AUTOTUNE=0 disables it (kernel heuristics).
 import os as _os
 
 _TUNED = {}
 _AUTOTUNE = _os.environ.get("STP3_CONV_AUTOTUNE", "1") != "0"
+_TUNE_PAIR = _os.environ.get("STP3_CONV_PAIR", "1") != "0"
 TUNE_LOG = []      # (description, {config: ms}) for reports
 
 
 def _tune(key, desc, launch, groupable):
     cands = [(1, 1), (2, 1)] + ([(1, 3), (2, 3)] if groupable else [])
+    if _TUNE_PAIR:
+        cands += [(3, 1)] + ([(3, 3)] if groupable else [])
     times = {}
     for ns, g in cands:
         launch(ns, g)                                   # warm (descriptor / attribute setup)
@@ -158,9 +161,10 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
          out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
-         head: Optional[dict] = None, store: bool = True) -> Optional[HL]:
+         head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
-    img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table())."""
+    img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table()).
+    tune = (n_sub, group) forces a tiling (n_sub 3 = CTA pair) instead of the autotuned one."""
     B, T_total, H, W, cs = x.hi.shape
     t0, T = frames if frames is not None else (0, T_total)      # process frames [t0, t0+T) of every sample
     Ho, Wo = out_hw if out_hw is not None else ((H + pc.stride - 1) // pc.stride, (W + pc.stride - 1) // pc.stride)
@@ -213,7 +217,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
 
     key = (pc.w.data_ptr(), B, T, H, W, cs, cin_off, Ho, Wo, t0, int(relu), residual is not None, out_f32 is not None,
            hd is not None)
-    cfg = _TUNED.get(key)
+    cfg = tune if tune is not None else _TUNED.get(key)
     if cfg is None and _AUTOTUNE and not torch.cuda.is_current_stream_capturing():
         taps = pc.taps
         groupable = pc.stride == 1 and len(taps) % 3 == 0 and all(

@@ -107,17 +107,22 @@ class TemporalBlock(PackedModule):
         # fused entry convolutions of paths 0 and 1 (N = 128: path 0 at rows 0.., path 1 at rows 64..)
         w0, b0 = dense.fold_bn(p0[0].conv.weight, p0[0].norm)
         w1, b1 = dense.fold_bn(p1[0].conv.weight, p1[0].norm)
-        wa = torch.zeros(128, cin, device=w0.device)
-        ba = torch.zeros(128, device=w0.device)
-        wa[:half], wa[64:64 + half] = flat(w0), flat(w1)
-        ba[:half], ba[64:64 + half] = b0, b1
-        P["a1"] = dense.pack_conv(wa[:, :cs].reshape(128, cs, 1, 1).contiguous(), ba, bn=128)
+        # path 0 lives at channel 0 of `mid`; path 1 right behind it when both fit one 64-channel K block (block 2 of
+        # the reference: 32 + 32), else in the next block (block 1: 35 + 35)
+        m1 = half if 2 * half <= 64 else 64
+        nmid = 64 if m1 == half else 128
+        P["m1"], P["nmid"] = m1, nmid
+        wa = torch.zeros(nmid, cin, device=w0.device)
+        ba = torch.zeros(nmid, device=w0.device)
+        wa[:half], wa[m1:m1 + half] = flat(w0), flat(w1)
+        ba[:half], ba[m1:m1 + half] = b0, b1
+        P["a1"] = dense.pack_conv(wa[:, :cs].reshape(nmid, cs, 1, 1).contiguous(), ba, bn=nmid)
         w2, b2 = dense.fold_bn(p2.conv.weight, p2.norm)
         P["a2"] = dense.pack_conv(flat(w2)[:, :cs].reshape(half, cs, 1, 1).contiguous(), b2, bn=64)
         wt, bt = dense.fold_bn(p0[1].conv.weight, p0[1].norm)          # (half, half, 2, 3, 3)
         P["b"] = dense.pack_conv(wt, bt, cin_p=64, bn=64)
         ws, bs = dense.fold_bn(p1[1].conv.weight, p1[1].norm)          # (half, half, 1, 3, 3)
-        P["c"] = dense.pack_conv(ws, bs, cin_p=64, bn=64)
+        P["c"] = dense.pack_conv(ws, bs, cin_p=64, bn=64, in_layout=[(0, half, m1 % 64)])
         wg, bg = dense.fold_bn(self.aggregation[0].conv.weight, self.aggregation[0].norm)
         wg = flat(wg)
         P["agg"] = dense.pack_conv(wg[:, :3 * half].reshape(cout, 3 * half, 1, 1).contiguous(), bg,
@@ -158,11 +163,12 @@ class TemporalBlock(PackedModule):
             return b
 
         mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
+        m1 = P["m1"]
         agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=128)
         if 3 * o < 128:
             agg.hi[..., 3 * o:].zero_(); agg.lo[..., 3 * o:].zero_()      # padding channels of the concat tensor
         dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
-        dense.conv(mid, P["c"], cin_off=64, out=agg, out_coff=o, n_store=o, relu=True)
+        dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
         dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=o, relu=True, img_bias=const_bias(P.get("a2_c"), P["a2"]))
         pbias = None
         if self.use_pyramid_pooling:

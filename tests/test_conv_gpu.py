@@ -73,6 +73,45 @@ def test_conv2d_matches_fp64(cin, cout, k, stride, dil, hw):
         assert float((y.hi[..., cout:].float().abs() + y.lo[..., cout:].float().abs()).max()) == 0.0
 
 
+@pytest.mark.parametrize("tune", [(1, 1), (2, 1), (1, 3), (2, 3), (3, 1), (3, 3)])
+@pytest.mark.parametrize("cin,cout,k,dil,hw", [
+    (64, 128, 3, 1, (40, 37)),        # weights streamed through the ring, partial tiles in x and y
+    (128, 64, 3, 1, (24, 24)),        # two K blocks
+    (64, 64, 1, 1, (50, 50)),         # resident weights
+    (64, 256, 3, 2, (33, 33)),        # dilation 2, BN = 256 (two launches)
+])
+def test_every_tiling_matches_fp64(tune, cin, cout, k, dil, hw):
+    """Every tiling the autotuner may pick -- 8x16 / 16x16 tiles per CTA, the 16x16 tile of a CTA pair
+    (tcgen05.mma.cta_group::2, n_sub = 3), with and without the shared dy-tap activation load -- gives the same
+    result."""
+    if tune[1] == 3 and (k != 3 or dil != 1):
+        pytest.skip("taps are not groupable")
+    H, W = hw
+    x = rnd(1, 3, cin, H, W, seed=31)
+    w = rnd(cout, cin, k, k, seed=32, scale=(cin * k * k) ** -0.5)
+    b = rnd(cout, seed=33)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV), dilation=dil)
+    y = dense.conv(to_hl(x), pc, relu=True, tune=tune)
+    torch.cuda.synchronize()
+    check(from_hl(y, 0, cout), F.relu(ref_conv2d(x, w, b, dilation=dil)))
+
+
+def test_pair_tiling_with_fused_epilogues():
+    """CTA-pair tiling with residual, per-image bias and odd image sizes (the peer CTA's rows fall off the image)."""
+    B, T, C, H, W = 2, 2, 64, 9, 21
+    x = rnd(B, T, C, H, W, seed=41)
+    w = rnd(64, C, 3, 3, seed=42, scale=0.05)
+    b = rnd(64, seed=43)
+    res = rnd(B, T, 64, H, W, seed=44)
+    ib = rnd(B * T, 64, seed=45)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    base = ref_conv2d(x, w, b) + ib.view(B, T, 64, 1, 1).double()
+    ib = ib + b.view(1, 64)
+    for tune in ((3, 1), (3, 3)):
+        y = dense.conv(to_hl(x), pc, relu=True, img_bias=ib.to(DEV), residual=to_hl(res), res_after_act=True, tune=tune)
+        check(from_hl(y), F.relu(base) + res.double())
+
+
 def test_causal_conv3d():
     """CausalConv3d (2,3,3): time padded on the left only (temporal.py:252-273)."""
     B, T, C, H, W = 2, 3, 35, 24, 20
