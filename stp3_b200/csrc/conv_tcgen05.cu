@@ -62,6 +62,7 @@ struct ConvParams {
   __nv_bfloat16* out_hi;    // channels-last (n_img, Ho, Wo, out_cstride), may be null when out_f32 is used
   __nv_bfloat16* out_lo;
   int out_cstride, out_coff, n_store;
+  int vec256;               // bit 0: output rows / windows are 32-byte aligned (256-bit stores), bit 1: residual likewise
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
   int n_valid, f32_coff;    // channel offset of this launch inside out_f32
   int sigmoid;              // apply to out_f32 (instance_center head)
@@ -82,7 +83,7 @@ struct ConvSmem {
   static constexpr int kBTileBytes = 2 * kBRows * kBK * 2;             // B_hi + B_lo of one K step
   static constexpr int kTmemCols = 4 * BN;                             // 2 sub-tiles x 2 accumulator buffers
   static constexpr size_t tail_bytes() {
-    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) +
+    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + kEpiWarps * 64 * sizeof(float) +
            (2 * kMaxAStages + 2 * kMaxBStages + 8) * 8;
   }
 };
@@ -123,7 +124,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(b_ring + (size_t)(resident ? k_iters : p.nb_stages) * S::kBTileBytes);
   float* s_head = s_bias + BN;                    // [kMaxHeadOut][BN]
   float* s_hx = s_head + kMaxHeadOut * BN;        // [kMaxHeadOut][128] head partials handed between column halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hx + kMaxHeadOut * 128);
+  float* s_wb = s_hx + kMaxHeadOut * 128;         // [kEpiWarps][64] per-image bias slice of each epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + kEpiWarps * 64);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxAStages;
   uint64_t* b_full = a_empty + kMaxAStages;
@@ -317,11 +319,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
       const int oy_t = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
-      const float* ib = p.img_bias ? p.img_bias + (size_t)img * p.img_bias_stride : nullptr;
+      // latency hiding: the residual of the first chunk and this warp's slice of the per-image bias are requested
+      // before waiting for the accumulator; every later residual chunk is requested one chunk ahead
+      const int n_sub_eff = PAIR ? 1 : p.n_sub;
+      uint32_t nh[8], nl[8];
+      auto request_residual = [&](int sub, int j) {
+        const int oy = oy_t + sub * kSubH + (r >> 4);
+        if (oy < p.Ho && ox < p.Wo) {
+          const size_t off = (((size_t)img * p.Ho + oy) * p.Wo + ox) * p.res_cstride + p.res_coff + col0 + j * 16;
+          if (p.vec256 & 2) {
+            ptx::ld_global_nc_v8(p.res_hi + off, nh);
+            ptx::ld_global_nc_v8(p.res_lo + off, nl);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + g);
+              const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + g);
+              nh[4 * g] = h4.x; nh[4 * g + 1] = h4.y; nh[4 * g + 2] = h4.z; nh[4 * g + 3] = h4.w;
+              nl[4 * g] = l4.x; nl[4 * g + 1] = l4.y; nl[4 * g + 2] = l4.z; nl[4 * g + 3] = l4.w;
+            }
+          }
+        }
+      };
+      if (p.res_mode) request_residual(0, 0);
+      const float* bsrc = s_bias;                 // bias of column c at bsrc[c]
+      if (p.img_bias) {
+        const float* ib = p.img_bias + (size_t)img * p.img_bias_stride + col0;
+        float* wb = s_wb + e * 64;
+        __syncwarp();                             // every lane is done with the previous tile's slice
+#pragma unroll
+        for (int i = lane; i < kColsPerWarp; i += 32) wb[i] = __ldg(ib + i);
+        __syncwarp();
+        bsrc = wb - col0;
+      }
       ptx::mbar_wait(&tmem_full_bar[buf], acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < (PAIR ? 1 : p.n_sub); ++sub) {
+      for (int sub = 0; sub < n_sub_eff; ++sub) {
         const int oy = oy_t + sub * kSubH + (r >> 4);
         const bool valid = oy < p.Ho && ox < p.Wo;
         const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
@@ -334,55 +368,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           const int cb = col0 + j * 16;              // first output channel of this chunk
           uint32_t acc[16];
           ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+          uint32_t rhw[8], rlw[8];                   // residual of this chunk (requested one chunk ago)
+          if (p.res_mode) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { rhw[i] = nh[i]; rlw[i] = nl[i]; }
+            const bool last_j = j + 1 == kColsPerWarp / 16;
+            if (!last_j) request_residual(sub, j + 1);
+            else if (sub + 1 < n_sub_eff) request_residual(sub + 1, 0);
+          }
           ptx::tmem_ld_wait();
           if (valid) {
             float v[16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {          // bias: per-image table (conv bias already folded in) or smem
-              const float4 b4 = ib ? __ldg(reinterpret_cast<const float4*>(ib + cb) + g)
-                                   : *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
+            for (int g = 0; g < 4; ++g) {          // bias: per-image slice (conv bias already folded in) or the conv's own
+              const float4 b4 = *reinterpret_cast<const float4*>(bsrc + cb + 4 * g);
               v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
               v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
               v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
               v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
             }
             if (p.res_mode) {
-              const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.res_cstride + p.res_coff + cb);
-              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.res_cstride + p.res_coff + cb);
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                  const float r0 = __uint_as_float(hw[e2] << 16) + __uint_as_float(lw[e2] << 16);
-                  const float r1 = __uint_as_float(hw[e2] & 0xFFFF0000u) + __uint_as_float(lw[e2] & 0xFFFF0000u);
-                  float& a0 = v[g * 8 + e2 * 2], &a1 = v[g * 8 + e2 * 2 + 1];
-                  if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
-                  else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
-                }
+              for (int e2 = 0; e2 < 8; ++e2) {
+                const float r0 = __uint_as_float(rhw[e2] << 16) + __uint_as_float(rlw[e2] << 16);
+                const float r1 = __uint_as_float(rhw[e2] & 0xFFFF0000u) + __uint_as_float(rlw[e2] & 0xFFFF0000u);
+                float& a0 = v[e2 * 2], &a1 = v[e2 * 2 + 1];
+                if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
+                else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
               }
             } else if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.out_hi) {
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.out_cstride + p.out_coff + cb);
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.out_cstride + p.out_coff + cb);
+            if (p.out_hi && cb < p.n_store) {
+              __nv_bfloat16* ohp = p.out_hi + pix * p.out_cstride + p.out_coff + cb;
+              __nv_bfloat16* olp = p.out_lo + pix * p.out_cstride + p.out_coff + cb;
+              uint32_t hw[8], lw[8];
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                if (cb + g * 8 >= p.n_store) break;
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                  const float x0 = v[g * 8 + e2 * 2], x1 = v[g * 8 + e2 * 2 + 1];
-                  const uint32_t h = ptx::pack_bf16x2(x0, x1);                 // one cvt.rn.bf16x2.f32
-                  const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
-                  hw[e2] = h;
-                  lw[e2] = ptx::pack_bf16x2(r0, r1);
+              for (int e2 = 0; e2 < 8; ++e2) {
+                const float x0 = v[e2 * 2], x1 = v[e2 * 2 + 1];
+                const uint32_t h = ptx::pack_bf16x2(x0, x1);                   // one cvt.rn.bf16x2.f32
+                const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xFFFF0000u);
+                hw[e2] = h;
+                lw[e2] = ptx::pack_bf16x2(r0, r1);
+              }
+              if ((p.vec256 & 1) && cb + 16 <= p.n_store) {     // one full 32-byte sector per plane and lane
+                ptx::st_global_v8(ohp, hw);
+                ptx::st_global_v8(olp, lw);
+              } else {
+                reinterpret_cast<uint4*>(ohp)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                reinterpret_cast<uint4*>(olp)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                if (cb + 8 < p.n_store) {
+                  reinterpret_cast<uint4*>(ohp)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                  reinterpret_cast<uint4*>(olp)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
                 }
-                oh[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                ol[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }
             }
             if (p.out_f32) {
@@ -599,6 +638,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     p.out_coff = d->out_coff + coff;
     p.n_store = n_store - coff < bn_launch ? (n_store - coff > 0 ? n_store - coff : 0) : bn_launch;
     p.f32_coff = coff;
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    p.vec256 = (y_hi && d->out_cstride % 16 == 0 && p.out_coff % 16 == 0 && al32(y_hi) && al32(y_lo) ? 1 : 0) |
+               (d->res_mode && d->res_cstride % 16 == 0 && p.res_coff % 16 == 0 && al32(res_hi) && al32(res_lo) ? 2 : 0);
 #define STP3_LAUNCH_CONV(BN_, PAIR_)                                                                              \
     do {                                                                                                          \
       using SM = ConvSmem<BN_, PAIR_>;                                                                            \
