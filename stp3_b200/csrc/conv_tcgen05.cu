@@ -137,6 +137,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: the next conv of the stream may set up (barriers, TMEM, resident weights) on SMs
+  // this grid has left; this grid's own set-up ran while its predecessor drained.  Only module constants (bias,
+  // weights, head weights) are read before griddep_wait().
+  ptx::griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
     for (int i = 0; i < p.na_stages; ++i) { ptx::mbar_init(&a_full[i], kProd); ptx::mbar_init(&a_empty[i], 1); }
@@ -187,6 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
       }
       __syncwarp();
+      ptx::griddep_wait();                        // activations come from the preceding kernel
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
         const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
@@ -316,6 +321,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int col0 = half * kColsPerWarp;
     const int r = q * 32 + lane;                 // row of the sub-tile = output pixel
     int buf = 0; uint32_t acc_phase = 0;
+    ptx::griddep_wait();                          // residual / per-image bias reads and every global write come after
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
       const int oy_t = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
@@ -543,7 +549,10 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   static const int env_nsub = [] { const char* e = getenv("STP3_CONV_NSUB"); return e ? atoi(e) : 0; }();
   static const int env_group = [] { const char* e = getenv("STP3_CONV_GROUP"); return e ? atoi(e) : 0; }();
   const int want_nsub = d->tune_n_sub ? d->tune_n_sub : env_nsub;
-  const int want_group = d->tune_group ? d->tune_group : env_group;
+  const int want_group_raw = d->tune_group ? d->tune_group : env_group;
+  const int want_group = want_group_raw & 3;
+  static const bool use_pdl = [] { const char* e = getenv("STP3_CONV_PDL"); return !e || atoi(e) != 0; }();
+  const bool stream_weights = (want_group_raw & 4) != 0;    // +4: keep the weights in the ring even if they would fit
   // taps that can share one activation load: consecutive triples (same dt, dx; dy, dy+1, dy+2) of a stride-1 kernel
   int group = 1;
   if (d->stride == 1 && d->ntaps % 3 == 0 && want_group != 1) {
@@ -647,7 +656,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       const size_t avail = smem_cap - 1024 - SM::tail_bytes();                                                    \
       const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                    \
       /* small weight tensors stay resident in smem next to >= 2 activation stages */                            \
-      const bool res = wbytes + 2 * a_stage <= avail;                                                             \
+      const bool res = !stream_weights && wbytes + 2 * a_stage <= avail;                                          \
       int na, nb;                                                                                                 \
       if (res) {                                                                                                  \
         na = (int)((avail - wbytes) / a_stage); nb = 0;                                                           \
@@ -670,7 +679,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       cudaLaunchConfig_t cfg = {};                                                                                \
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads);                                                \
       cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;                                                     \
-      cudaLaunchAttribute attr[1];                                                                                \
+      cudaLaunchAttribute attr[2];                                                                                \
       attr[0].id = cudaLaunchAttributeClusterDimension;                                                           \
       attr[0].val.clusterDim.x = PAIR_ ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;       \
       cfg.attrs = attr; cfg.numAttrs = PAIR_ ? 1 : 0;                                                             \
@@ -680,6 +689,13 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
         STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));                                  \
         if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");             \
         if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;             \
+      }                                                                                                           \
+      if (use_pdl) {                                                                                              \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+        attr[1].id = cudaLaunchAttributeClusterDimension;                                                         \
+        attr[1].val.clusterDim.x = PAIR_ ? 2 : 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;     \
+        cfg.numAttrs = PAIR_ ? 2 : 1;                                                                             \
       }                                                                                                           \
       STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));                                        \
     } while (0)

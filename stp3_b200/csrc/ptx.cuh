@@ -80,6 +80,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel of the stream (launched with programmatic stream serialization) may start its
+// prologue once every CTA of this grid has passed this point or exited.  wait: blocks until the preceding grid has
+// completed and flushed its memory; everything that reads or writes dependent global memory comes after it.  Both
+// are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- thread-block clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

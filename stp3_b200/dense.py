@@ -137,10 +137,12 @@ _TUNE_PAIR = _os.environ.get("STP3_CONV_PAIR", "1") != "0"
 TUNE_LOG = []      # (description, {config: ms}) for reports
 
 
-def _tune(key, desc, launch, groupable):
+def _tune(key, desc, launch, groupable, ntaps=1):
     cands = [(1, 1), (2, 1)] + ([(1, 3), (2, 3)] if groupable else [])
     if _TUNE_PAIR:
         cands += [(3, 1)] + ([(3, 3)] if groupable else [])
+    if ntaps > 1:       # weights streamed through the ring instead of resident: more activation stages in flight
+        cands += [(ns, g + 4) for ns, g in cands if ns != 1]
     times = {}
     for ns, g in cands:
         launch(ns, g)                                   # warm (descriptor / attribute setup)
@@ -224,7 +226,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
             taps[i + j][0] == taps[i][0] and taps[i + j][2] == taps[i][2] and taps[i + j][1] == taps[i][1] + j
             for i in range(0, len(taps), 3) for j in (1, 2))
         desc = f"{len(taps)}tap cin{pc.cin_p} bn{pc.bn} s{pc.stride} {B * T}x{Ho}x{Wo}"
-        cfg = _tune(key, desc, launch, groupable)
+        cfg = _tune(key, desc, launch, groupable, len(taps))
     launch(*(cfg or (0, 0)))
     return out
 
