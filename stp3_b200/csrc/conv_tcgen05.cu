@@ -40,6 +40,8 @@ constexpr int kMaxHeadOut = 8;
 
 struct ConvParams {
   int n_img, T, t0, Ho, Wo;
+  int T_total;              // frames of the input tensor
+  int skip_t;               // skip tap groups whose frame lies outside [0, T_total): they only multiply zero padding
   int tiles_x, tiles_y, n_tiles;
   int stride;
   int kblocks;              // Cin / 64 of this convolution
@@ -202,6 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           const int x = ox0 * p.stride + p.tap[tap0][2];
           const int y = oy0 * p.stride + p.tap[tap0][1];
           const int t = tidx + p.tap[tap0][0];
+          if (p.skip_t && (t < 0 || t >= p.T_total)) continue;     // causal padding in time: nothing to add
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&a_empty[as], aph ^ 1);
             if (ptx::elect_one_sync()) {
@@ -266,7 +269,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         wait_full(&tmem_empty_bar[buf], acc_phase ^ 1);           // the epilogue has drained this accumulator pair
         ptx::tc_fence_after();
         uint32_t accumulate = 0;
+        const int tidx = p.t0 + (tile / tiles_per_img) % p.T;
         for (int grp = 0; grp < n_groups; ++grp) {
+          if (p.skip_t) {
+            const int t = tidx + p.tap[grp * p.group][0];
+            if (t < 0 || t >= p.T_total) continue;
+          }
           for (int kb = 0; kb < p.kblocks; ++kb) {
             wait_full(&a_full[as], aph);
             ptx::tc_fence_after();
@@ -606,6 +614,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 
   ConvParams p;
   p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.T_total = T_total;
+  p.skip_t = 0;                                     // safe only if some tap always stays inside (dt == 0)
+  for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0) p.skip_t = 1;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
   p.group = group; p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;

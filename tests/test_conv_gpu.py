@@ -112,14 +112,16 @@ def test_pair_tiling_with_fused_epilogues():
         check(from_hl(y), F.relu(base) + res.double())
 
 
-def test_causal_conv3d():
-    """CausalConv3d (2,3,3): time padded on the left only (temporal.py:252-273)."""
+@pytest.mark.parametrize("tune", [None, (1, 1), (2, 3), (3, 1), (3, 3), (3, 7), (2, 5)])
+def test_causal_conv3d(tune):
+    """CausalConv3d (2,3,3): time padded on the left only (temporal.py:252-273); tap groups that only see the zero
+    padding in time (frame 0, dt = -1) are skipped by the kernel."""
     B, T, C, H, W = 2, 3, 35, 24, 20
     x = rnd(B, T, C, H, W, seed=4)
     w = rnd(35, C, 2, 3, 3, seed=5, scale=0.05)
     b = rnd(35, seed=6)
     pc = dense.pack_conv(w.to(DEV), b.to(DEV))
-    y = dense.conv(to_hl(x), pc, relu=True)
+    y = dense.conv(to_hl(x), pc, relu=True, tune=tune)
     xp = F.pad(x.permute(0, 2, 1, 3, 4).double(), (1, 1, 1, 1, 1, 0))
     ref = F.relu(F.conv3d(xp, w.double(), b.double())).permute(0, 2, 1, 3, 4)
     check(from_hl(y, 0, 35), ref)
