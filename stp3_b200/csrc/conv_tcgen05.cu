@@ -48,7 +48,11 @@ struct ConvParams {
   int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
   int ntaps;
   int n_sub;                // sub-tiles per tile: 2 (16x16 pixels, weight tiles shared) or 1 (small images: more tiles)
-  int group;                // taps that share one activation load: 3 = the three dy taps of a 3x3 (stride 1, dilation 1)
+  // taps that share one activation load: consecutive taps with the same (dt, dx) whose dy advance by the stride read
+  // the same strided rows shifted by one OUTPUT row each (the three dy taps of a 3x3; dy = -3,-1,1,3 / -2,0,2 of the
+  // stride-2 7x7), so one box of tile_rows + gmax - 1 rows serves the whole group
+  int n_groups, gmax;
+  unsigned char gstart[kMaxTaps], gsize[kMaxTaps];
   int a_plane_bytes;        // bytes of one activation plane of a stage = box_h * 16 px * 128 B
   int w_rows;               // rows per (tap, kb, plane) block of the packed weight tensor (the convolution's padded Cout)
   int w_row_off;            // first row of this launch inside that block (a 256-channel conv runs as two launches)
@@ -166,7 +170,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int n_groups = p.ntaps / p.group;
+  const int n_groups = p.n_groups;
   const int tile_h = PAIR ? 2 * kSubH : kSubH * p.n_sub;      // image rows of a tile (a pair: 8 per CTA)
 
   if (warp == 0) {
@@ -200,7 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int oy0 = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox0 = (rem % p.tiles_x) * kTileW;
         const int bidx = img / p.T, tidx = p.t0 + img % p.T;
         for (int grp = 0; grp < n_groups; ++grp) {
-          const int tap0 = grp * p.group;
+          const int tap0 = p.gstart[grp], gsz = p.gsize[grp];
           const int x = ox0 * p.stride + p.tap[tap0][2];
           const int y = oy0 * p.stride + p.tap[tap0][1];
           const int t = tidx + p.tap[tap0][0];
@@ -224,7 +228,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             __syncwarp();
             if (++as == p.na_stages) { as = 0; aph ^= 1; }
             if (!resident) {
-              for (int j = 0; j < p.group; ++j) {
+              for (int j = 0; j < gsz; ++j) {
                 const int it = (tap0 + j) * p.kblocks + kb;          // [tap][kb][plane][rows] blocks of 64-wide rows
                 ptx::mbar_wait(&b_empty[bs], bph ^ 1);
                 if (ptx::elect_one_sync()) {
@@ -272,15 +276,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int tidx = p.t0 + (tile / tiles_per_img) % p.T;
         for (int grp = 0; grp < n_groups; ++grp) {
           if (p.skip_t) {
-            const int t = tidx + p.tap[grp * p.group][0];
+            const int t = tidx + p.tap[p.gstart[grp]][0];
             if (t < 0 || t >= p.T_total) continue;
           }
+          const int tap0 = p.gstart[grp], gsz = p.gsize[grp];
           for (int kb = 0; kb < p.kblocks; ++kb) {
             wait_full(&a_full[as], aph);
             ptx::tc_fence_after();
             const uint32_t a_hi0 = ptx::smem_u32(a_ring + (size_t)as * a_stage_bytes);
-            for (int j = 0; j < p.group; ++j) {
-              const int it = (grp * p.group + j) * p.kblocks + kb;
+            for (int j = 0; j < gsz; ++j) {
+              const int it = (tap0 + j) * p.kblocks + kb;
               uint32_t b_hi;
               if (resident) {
                 b_hi = ptx::smem_u32(b_ring + (size_t)it * S::kBTileBytes);
@@ -561,16 +566,21 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const int want_group = want_group_raw & 3;
   static const bool use_pdl = [] { const char* e = getenv("STP3_CONV_PDL"); return !e || atoi(e) != 0; }();
   const bool stream_weights = (want_group_raw & 4) != 0;    // +4: keep the weights in the ring even if they would fit
-  // taps that can share one activation load: consecutive triples (same dt, dx; dy, dy+1, dy+2) of a stride-1 kernel
-  int group = 1;
-  if (d->stride == 1 && d->ntaps % 3 == 0 && want_group != 1) {
-    group = 3;
-    for (int i = 0; i < d->ntaps && group == 3; i += 3)
-      for (int j = 1; j < 3; ++j)
-        if (d->taps[i + j][0] != d->taps[i][0] || d->taps[i + j][2] != d->taps[i][2] ||
-            d->taps[i + j][1] != d->taps[i][1] + j)
-          group = 1;
+  // taps that can share one activation load: runs (<= 4) of consecutive taps with the same (dt, dx) and dy advancing
+  // by the stride
+  ConvParams p;
+  p.n_groups = 0; p.gmax = 1;
+  for (int i = 0; i < d->ntaps;) {
+    int g = 1;
+    if (want_group != 1)
+      while (g < 4 && i + g < d->ntaps && d->taps[i + g][0] == d->taps[i][0] && d->taps[i + g][2] == d->taps[i][2] &&
+             d->taps[i + g][1] == d->taps[i][1] + g * d->stride)
+        ++g;
+    p.gstart[p.n_groups] = (unsigned char)i; p.gsize[p.n_groups] = (unsigned char)g; ++p.n_groups;
+    if (g > p.gmax) p.gmax = g;
+    i += g;
   }
+  const int group = p.gmax;
   // two sub-tiles per tile halve the weight traffic; small images keep one so that there are enough tiles
   const int n_img_ = d->B * d->T;
   const long long tiles16 = (long long)n_img_ * ceil_div(d->Wo, kTileW) * ceil_div(d->Ho, 2 * kSubH);
@@ -612,14 +622,13 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     if (r != CUDA_SUCCESS) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
 
-  ConvParams p;
   p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
   p.T_total = T_total;
   p.skip_t = 0;                                     // safe only if some tap always stays inside (dt == 0)
   for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0) p.skip_t = 1;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
-  p.group = group; p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
+  p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
   p.relu = d->relu; p.res_mode = d->res_mode;
   p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);

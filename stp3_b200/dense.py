@@ -100,8 +100,9 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     dev = weight.device
     taps, mats = [], []
     for it in range(kt):
-        for ix in range(kw):              # dy innermost: consecutive taps (dy, dy+1, dy+2) share one activation load
-            for iy in range(kh):
+        for ix in range(kw):              # dy innermost: runs of taps whose dy advance by the stride share one
+            # activation load (stride 1: dy, dy+1, dy+2; stride 2: the even rows of the kernel, then the odd ones)
+            for iy in (list(range(0, kh, 2)) + list(range(1, kh, 2)) if stride == 2 else range(kh)):
                 dy, dx = iy * dilation - pad_h, ix * dilation - pad_w
                 if prune_extent is not None and stride == 1:
                     # a tap whose shift exceeds the image reads only zero padding for every output pixel
@@ -222,9 +223,8 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
     cfg = tune if tune is not None else _TUNED.get(key)
     if cfg is None and _AUTOTUNE and not torch.cuda.is_current_stream_capturing():
         taps = pc.taps
-        groupable = pc.stride == 1 and len(taps) % 3 == 0 and all(
-            taps[i + j][0] == taps[i][0] and taps[i + j][2] == taps[i][2] and taps[i + j][1] == taps[i][1] + j
-            for i in range(0, len(taps), 3) for j in (1, 2))
+        groupable = any(taps[i + 1][0] == taps[i][0] and taps[i + 1][2] == taps[i][2] and
+                        taps[i + 1][1] == taps[i][1] + pc.stride for i in range(len(taps) - 1))
         desc = f"{len(taps)}tap cin{pc.cin_p} bn{pc.bn} s{pc.stride} {B * T}x{Ho}x{Wo}"
         cfg = _tune(key, desc, launch, groupable, len(taps))
     launch(*(cfg or (0, 0)))

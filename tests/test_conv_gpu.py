@@ -96,6 +96,21 @@ def test_every_tiling_matches_fp64(tune, cin, cout, k, dil, hw):
     check(from_hl(y, 0, cout), F.relu(ref_conv2d(x, w, b, dilation=dil)))
 
 
+@pytest.mark.parametrize("tune", [(1, 1), (1, 3), (2, 3), (3, 3), (3, 7)])
+@pytest.mark.parametrize("k,hw", [(7, (50, 46)), (3, (37, 41)), (5, (30, 30))])
+def test_stride2_tap_groups(tune, k, hw):
+    """Stride-2 kernels: the taps of one kernel column whose dy have the same parity share an activation load
+    (7x7: groups of 4 and 3; 3x3: 2 and 1); decoder.first_conv / the ResNet stride-2 3x3s (decoder.py:22-30)."""
+    H, W = hw
+    x = rnd(2, 2, 64, H, W, seed=51)
+    w = rnd(64, 64, k, k, seed=52, scale=(64 * k * k) ** -0.5)
+    b = rnd(64, seed=53)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV), stride=2)
+    y = dense.conv(to_hl(x), pc, relu=True, tune=tune)
+    torch.cuda.synchronize()
+    check(from_hl(y, 0, 64), F.relu(ref_conv2d(x, w, b, stride=2)))
+
+
 def test_pair_tiling_with_fused_epilogues():
     """CTA-pair tiling with residual, per-image bias and odd image sizes (the peer CTA's rows fall off the image)."""
     B, T, C, H, W = 2, 2, 64, 9, 21
