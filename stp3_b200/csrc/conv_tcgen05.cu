@@ -41,7 +41,9 @@ constexpr int kMaxHeadOut = 8;
 struct ConvParams {
   int n_img, T, t0, Ho, Wo;
   int T_total;              // frames of the input tensor
-  int skip_t;               // skip tap groups whose frame lies outside [0, T_total): they only multiply zero padding
+  int H, W;                 // input image size
+  int skip_t;               // skip tap groups whose window lies entirely in the zero padding for the whole tile (frame
+                            // outside [0, T_total): causal convs at t = 0; rows / columns outside the image: dilated convs)
   int tiles_x, tiles_y, n_tiles;
   int stride;
   int kblocks;              // Cin / 64 of this convolution
@@ -93,6 +95,18 @@ struct ConvSmem {
            (2 * kMaxAStages + 2 * kMaxBStages + 8) * 8;
   }
 };
+
+// true if every input element the tap group touches for this tile is zero padding (same answer in the producer and
+// the MMA issuer, and in both CTAs of a pair: it looks at the whole tile)
+__device__ __forceinline__ bool group_is_padding(const ConvParams& p, int grp, int tidx, int oy_tile, int ox0, int tile_h) {
+  const int tap0 = p.gstart[grp];
+  const int t = tidx + p.tap[tap0][0];
+  const int ylo = oy_tile * p.stride + p.tap[tap0][1];
+  const int yhi = (oy_tile + tile_h - 1 + p.gsize[grp] - 1) * p.stride + p.tap[tap0][1];
+  const int xlo = ox0 * p.stride + p.tap[tap0][2];
+  const int xhi = (ox0 + kTileW - 1) * p.stride + p.tap[tap0][2];
+  return t < 0 || t >= p.T_total || yhi < 0 || ylo >= p.H || xhi < 0 || xlo >= p.W;
+}
 
 // Persistent, warp-specialised implicit-GEMM convolution.
 //   * A CTA walks output tiles blockIdx.x + i*gridDim.x; a tile is 16x16 pixels = two M=128 sub-tiles that share every
@@ -208,7 +222,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           const int x = ox0 * p.stride + p.tap[tap0][2];
           const int y = oy0 * p.stride + p.tap[tap0][1];
           const int t = tidx + p.tap[tap0][0];
-          if (p.skip_t && (t < 0 || t >= p.T_total)) continue;     // causal padding in time: nothing to add
+          if (p.skip_t && group_is_padding(p, grp, tidx, oy0 - (int)rank * kSubH, ox0, tile_h)) continue;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&a_empty[as], aph ^ 1);
             if (ptx::elect_one_sync()) {
@@ -274,11 +288,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         ptx::tc_fence_after();
         uint32_t accumulate = 0;
         const int tidx = p.t0 + (tile / tiles_per_img) % p.T;
+        const int rem_m = tile % tiles_per_img;
+        const int oy_m = (rem_m / p.tiles_x) * tile_h, ox_m = (rem_m % p.tiles_x) * kTileW;
         for (int grp = 0; grp < n_groups; ++grp) {
-          if (p.skip_t) {
-            const int t = tidx + p.tap[p.gstart[grp]][0];
-            if (t < 0 || t >= p.T_total) continue;
-          }
+          if (p.skip_t && group_is_padding(p, grp, tidx, oy_m, ox_m, tile_h)) continue;
           const int tap0 = p.gstart[grp], gsz = p.gsize[grp];
           for (int kb = 0; kb < p.kblocks; ++kb) {
             wait_full(&a_full[as], aph);
@@ -624,8 +637,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 
   p.n_img = d->B * d->T; p.T = d->T; p.t0 = d->t0; p.Ho = d->Ho; p.Wo = d->Wo;
   p.T_total = T_total;
-  p.skip_t = 0;                                     // safe only if some tap always stays inside (dt == 0)
-  for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0) p.skip_t = 1;
+  p.H = d->H; p.W = d->W;
+  p.skip_t = 0;                                     // safe only if some tap always stays inside: the centre tap
+  for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0 && d->taps[i][1] == 0 && d->taps[i][2] == 0) p.skip_t = 1;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
   p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
