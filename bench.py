@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: serialise H2D, compute and D2H of every step")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the resident timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     cfg = syn.CONFIGS["perceive"]
 
@@ -335,7 +337,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     total_ms = timed(step_resident, K)
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     e2e_mode = "serial: H2D -> compute -> D2H per step"
     if graphed is not None and not args.no_pipeline:
         from stp3_b200.models.stp3 import PipelinedPerception

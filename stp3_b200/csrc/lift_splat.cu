@@ -471,6 +471,19 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
     int* rrow = s_rank + wl * HP + h;
     const float xw = inb ? __ldg(p.xs + w) : 0.f;
     const float yh = s_ys[h];
+    // loop invariants in registers: the camera transform, up to two ego-motion links (longer chains walk the
+    // shared-memory copies), the quantisation constants
+    float cm[12], e0[12], e1[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      cm[i] = s_mat[i];
+      e0[i] = n_chain > 0 ? s_mat[12 + i] : 0.f;
+      e1[i] = n_chain > 1 ? s_mat[24 + i] : 0.f;
+    }
+    const bool ivx = p.inv_ok[0] != 0, ivy = p.inv_ok[1] != 0, ivz = p.inv_ok[2] != 0;
+    const float inx = p.inv[0], iny = p.inv[1], inz = p.inv[2];
+    const int nyz = p.ny * p.nz, nzz = p.nz;
+    int32_t* rout = p.ranks_out ? p.ranks_out + ((size_t)img * D * Hf + h) * Wf + w : nullptr;
     for (int d = da; d < db; ++d) {
       int rank = -1;
       if (inb) {
@@ -478,18 +491,20 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
         float x = __fmul_rn(xw, dep);                  // stp3.py:195: (u*d, v*d, d)
         float y = __fmul_rn(yh, dep);
         float z = dep;
-        affine_exact(s_mat, s_mat + 9, x, y, z);       // stp3.py:196-198
-        for (int k = 0; k < n_chain; ++k)              // stp3.py:270-277, sequential, rounded every step
+        affine_exact(cm, cm + 9, x, y, z);             // stp3.py:196-198
+        if (n_chain > 0) affine_exact(e0, e0 + 9, x, y, z);     // stp3.py:270-277, sequential, rounded every step
+        if (n_chain > 1) affine_exact(e1, e1 + 9, x, y, z);
+        for (int k = 2; k < n_chain; ++k)
           affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
-        const float qx = p.inv_ok[0] ? __fmul_rn(__fsub_rn(x, offx), p.inv[0]) : __fdiv_rn(__fsub_rn(x, offx), resx);
-        const float qy = p.inv_ok[1] ? __fmul_rn(__fsub_rn(y, offy), p.inv[1]) : __fdiv_rn(__fsub_rn(y, offy), resy);
-        const float qz = p.inv_ok[2] ? __fmul_rn(__fsub_rn(z, offz), p.inv[2]) : __fdiv_rn(__fsub_rn(z, offz), resz);
+        const float qx = ivx ? __fmul_rn(__fsub_rn(x, offx), inx) : __fdiv_rn(__fsub_rn(x, offx), resx);
+        const float qy = ivy ? __fmul_rn(__fsub_rn(y, offy), iny) : __fdiv_rn(__fsub_rn(y, offy), resy);
+        const float qz = ivz ? __fmul_rn(__fsub_rn(z, offz), inz) : __fdiv_rn(__fsub_rn(z, offz), resz);
         const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
         if (keep) {
           const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi == .long() truncation
-          rank = ix * (p.ny * p.nz) + iy * p.nz + iz;              // stp3.py:251-255
+          rank = ix * nyz + iy * nzz + iz;                         // stp3.py:251-255
         }
-        if (p.ranks_out) p.ranks_out[(((size_t)img * D + d) * Hf + h) * Wf + w] = rank;
+        if (rout) rout[(size_t)d * Hf * Wf] = rank;
       }
       rrow[d * TW * HP] = rank;
     }
@@ -749,6 +764,126 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
   }
 }
 
+// Channels-last outputs (fp32 NHWC, or the bf16 hi/lo planes the tensor-core layers read): one thread = one pillar x
+// 16 channels, LPP = C/16 neighbouring lanes cover a pillar.  Every global access is a full 32-byte sector per lane
+// (LDG.256 / STG.256) and the lanes of a pillar touch one contiguous row -- the lane-per-pillar mapping of the kernel
+// above would write half sectors 128 bytes apart here.  Same arithmetic, same workspace-cleaning contract; the CTA
+// clears the occupancy bytes itself because it covers all channels of its pillars.
+template <int LPP, int SMAX>
+__global__ void __launch_bounds__(256)
+bev_finalize_cl_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, float* __restrict__ out,
+                       float* __restrict__ pool_sum, int S, int nvox, float discount, int out_layout) {
+  constexpr int C = LPP * 16, PPB = 256 / LPP;
+  __shared__ float s_pool[8][SMAX][C];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = tid % LPP, pcell = blockIdx.x * PPB + tid / LPP;
+  const int c0 = sub * 16;
+  const bool valid = pcell < nvox;
+  unsigned occ_bits = 0;
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t)
+    if (t < S && valid && occ[((size_t)b * S + t) * nvox + pcell]) occ_bits |= 1u << t;
+  // every grid load is issued before any store (see above)
+  uint32_t v[SMAX][16];
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[t][i] = 0u;
+    if (occ_bits & (1u << t)) {
+      const float* src = grid + (((size_t)b * S + t) * nvox + pcell) * C + c0;
+      uint32_t a[8], c[8];
+      ptx::ld_global_v8(src, a);
+      ptx::ld_global_v8(src + 8, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[t][i] = a[i]; v[t][8 + i] = c[i]; }
+    }
+  }
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    if (t < S) {
+      const size_t bt = (size_t)b * S + t;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = __fadd_rn(__fmul_rn(acc[i], discount), __uint_as_float(v[t][i]));
+      if (valid) {
+        if (out_layout == 2) {
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(out) + (bt * nvox + pcell) * C + c0;
+          __nv_bfloat16* lp = hp + (size_t)gridDim.y * S * nvox * C;
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float x0 = acc[2 * e], x1 = acc[2 * e + 1];
+            const uint32_t h = ptx::pack_bf16x2(x0, x1);
+            hw[e] = h;
+            lw[e] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+          }
+          ptx::st_global_v8(hp, hw);
+          ptx::st_global_v8(lp, lw);
+        } else {
+          float* dst = out + (bt * nvox + pcell) * C + c0;
+          uint32_t w0[8], w1[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(acc[i]); w1[i] = __float_as_uint(acc[8 + i]); }
+          ptx::st_global_v8(dst, w0);
+          ptx::st_global_v8(dst + 8, w1);
+        }
+      }
+      if (pool_sum) {
+        // sum over the 32/LPP pillars of the warp: halving butterfly (lanes that differ in `off` split the channels)
+        float sv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sv[i] = acc[i];
+        int base = 0;
+        int n = 16;
+#pragma unroll
+        for (int off = LPP; off < 32; off <<= 1) {
+          const bool upper = (lane & off) != 0;
+          const int half = n >> 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < half) {
+              const float send = upper ? sv[i] : sv[i + half];
+              const float keep = upper ? sv[i + half] : sv[i];
+              sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (upper) base += half;
+          n = half;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < n) s_pool[warp][t][c0 + base + i] = sv[i];
+      }
+    }
+  }
+  // leave the workspace clean: zero exactly the rows that were read, then the occupancy bytes
+  const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    if (occ_bits & (1u << t)) {
+      float* src = grid + (((size_t)b * S + t) * nvox + pcell) * C + c0;
+      ptx::st_global_v8(src, z);
+      ptx::st_global_v8(src + 8, z);
+    }
+  }
+  __syncthreads();
+  if (sub == 0)
+    for (int t = 0; t < S; ++t)
+      if (occ_bits & (1u << t)) occ[((size_t)b * S + t) * nvox + pcell] = 0;
+  if (pool_sum) {
+    for (int i = tid; i < S * C; i += 256) {
+      const int t = i / C, c = i % C;
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += s_pool[w][t][c];
+      pool_sum[(((size_t)b * gridDim.x + blockIdx.x) * S + t) * C + c] = a;
+    }
+  }
+}
+
 // pool_sum[b,t,c] += sum over a slice of the finalize CTAs' partials (B, nblk, S, C); grid (B*S, kPoolSlices),
 // block (32, 8).  All loads of a thread are issued before the partials are zeroed again (the whole workspace stays
 // all-zero between calls); pool_sum is cleared by the caller (cudaMemsetAsync in stp3_lift_splat_fwd).
@@ -967,18 +1102,30 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
   const int groups = ceil_div(C, 64);                 // 8 warps x 8 channels per CTA
   dim3 fgrid(ceil_div(nvox, 32), Bw, groups), fblock(32, C >= 64 ? 8 : ceil_div(C, 8));
   float* pool_part = pool_sum ? reinterpret_cast<float*>(p.occ + occ_bytes(Bw, Sw, nx, ny)) : nullptr;
+  // channels-last outputs with 32 / 64 / 128 channels and few frames: sector-exact kernel (one thread = 16 channels)
+  const bool cl = out_layout != 0 && (C == 32 || C == 64 || C == 128) && Sw <= 4;
+  int pool_blocks = ceil_div(nvox, 32);
+  if (cl) {
+    const int ppb = 256 / (C / 16);
+    pool_blocks = ceil_div(nvox, ppb);
+    dim3 cgrid(pool_blocks, Bw);
+    if (C == 32) bev_finalize_cl_kernel<2, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
+    else if (C == 64) bev_finalize_cl_kernel<4, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
+    else bev_finalize_cl_kernel<8, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
+  } else {
 #define STP3_FINALIZE(VEC, SMAX) \
   bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, C, nvox, discount, out_layout)
   if (C % 8 == 0) { if (Sw <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
   else            { if (Sw <= 4) STP3_FINALIZE(false, 4); else STP3_FINALIZE(false, 8); }
 #undef STP3_FINALIZE
+  }
   STP3_CUDA_OK(cudaGetLastError());
   if (pool_sum) {
     STP3_CUDA_OK(cudaMemsetAsync(pool_sum, 0, (size_t)Bw * Sw * C * sizeof(float), stream));
-    pool_reduce_kernel<<<dim3(Bw * Sw, kPoolSlices), dim3(32, 8), 0, stream>>>(pool_part, ceil_div(nvox, 32), Sw, C, pool_sum);
+    pool_reduce_kernel<<<dim3(Bw * Sw, kPoolSlices), dim3(32, 8), 0, stream>>>(pool_part, pool_blocks, Sw, C, pool_sum);
     STP3_CUDA_OK(cudaGetLastError());
   }
-  if (groups > 1) {
+  if (groups > 1 && !cl) {
     const size_t nocc = ((size_t)Bw * Sw * nvox + 255) & ~(size_t)255;
     clear_bytes_kernel<<<(unsigned)((nocc / 16 + 255) / 256), 256, 0, stream>>>(p.occ, nocc);
     STP3_CUDA_OK(cudaGetLastError());

@@ -165,11 +165,15 @@ class TemporalBlock(PackedModule):
         mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
         m1 = P["m1"]
         agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=128)
-        if 3 * o < 128:
-            agg.hi[..., 3 * o:].zero_(); agg.lo[..., 3 * o:].zero_()      # padding channels of the concat tensor
         dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
         dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
-        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=o, relu=True, img_bias=const_bias(P.get("a2_c"), P["a2"]))
+        # the last path also fills the padding channels of the concat tensor: its own padded output columns are exact
+        # zeros (zero weights and bias), so storing 128 - 2*o of them saves a separate fill
+        tail = min(64, 128 - 2 * o)
+        if 2 * o + tail < 128:                                   # narrow blocks (half < 25): fill what a2 cannot reach
+            agg.hi[..., 2 * o + tail:].zero_(); agg.lo[..., 2 * o + tail:].zero_()
+        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=tail, relu=True,
+                   img_bias=const_bias(P.get("a2_c"), P["a2"]))
         pbias = None
         if self.use_pyramid_pooling:
             ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
