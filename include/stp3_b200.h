@@ -127,7 +127,8 @@ typedef struct stp3_conv_desc {
   int sigmoid;           /* apply a sigmoid to y_f32 (instance_center head, decoder.py:70) */
   int tune_n_sub;        /* 0 = automatic; 1 / 2 = sub-tiles (8x16 pixels each) per CTA tile; 3 = 16x16 tile of a CTA pair (cta_group::2) */
   int tune_group;        /* 0 = automatic; 1 = never share an activation load between the dy taps of a 3x3; 3 = share;
-                            +4 = stream the weights through the smem ring even if they would fit (more activation stages) */
+                            +4 = stream the weights through the smem ring even if they would fit (more activation stages);
+                            +8 = (bn 64) one stacked [W_hi; W_lo] operand: 2 MMAs per product instead of 3 */
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:

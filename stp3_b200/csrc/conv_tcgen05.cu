@@ -85,11 +85,17 @@ struct ConvParams {
   int head_sigmoid_mask;    // bit k: sigmoid on output k
 };
 
-template <int BN, bool PAIR = false>
+// STACK (BN = 64 only): the hi and lo weight planes of a K step form ONE B operand of 2*BN rows, so a product is two
+// MMAs instead of three -- A_hi x [W_hi; W_lo] (N = 2*BN) and A_lo x W_hi (N = BN) -- and the activation tile is read
+// from shared memory twice instead of three times (N = 64 MMAs are bound by exactly those reads).  The accumulator
+// has 2*BN columns; the epilogue adds columns c and BN + c.
+template <int BN, bool PAIR = false, bool STACK = false>
 struct ConvSmem {
   static constexpr int kBRows = PAIR ? BN / 2 : BN;                    // weight rows held by one CTA (a pair splits N)
-  static constexpr int kBTileBytes = 2 * kBRows * kBK * 2;             // B_hi + B_lo of one K step
-  static constexpr int kTmemCols = 4 * BN;                             // 2 sub-tiles x 2 accumulator buffers
+  // B_hi + B_lo of one K step; a stacked pair holds [own half of the stacked operand (BN rows)][own half of W_hi]
+  static constexpr int kBTileBytes = (STACK && PAIR ? 3 : 2) * kBRows * kBK * 2;
+  static constexpr int kAccCols = STACK ? 2 * BN : BN;                 // TMEM columns of one accumulator
+  static constexpr int kTmemCols = 4 * kAccCols;                       // 2 sub-tiles x 2 accumulator buffers
   static constexpr size_t tail_bytes() {
     return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + kEpiWarps * 64 * sizeof(float) +
            (2 * kMaxAStages + 2 * kMaxBStages + 8) * 8;
@@ -123,11 +129,12 @@ __device__ __forceinline__ bool group_is_padding(const ConvParams& p, int grp, i
 // operand reads per MMA drop by a quarter and the weight traffic per SM halves.  Barrier protocol: "full" barriers
 // live in the leader and collect the TMA bytes of both CTAs; "empty" / "accumulator ready" are multicast commits;
 // "accumulator drained" collects the epilogue warps of both CTAs in the leader.
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool STACK>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
-  using S = ConvSmem<BN, PAIR>;
+  using S = ConvSmem<BN, PAIR, STACK>;
+  static_assert(!STACK || BN == 64, "stacked weight operand: BN = 64 only (TMEM columns)");
   constexpr int kBRows = S::kBRows;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;              // 0 = leader
   const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a pair walks together)
@@ -190,25 +197,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loops; one elected lane issues) =====================
     {
-      // in a pair every "full" barrier is the leader's: arrive / complete_tx go through its shared::cluster address
-      const int w_row0 = p.w_row_off + (int)rank * kBRows;
-      if (resident && ptx::elect_one_sync()) {
+      // in a pair every "full" barrier is the leader's: arrive / complete_tx go through its shared::cluster address.
+      // load_b: the weight tile of K step `it` into `dst` (called by the elected lane; transaction bytes on `bar`)
+      auto load_b = [&](unsigned char* dst, int it, uint64_t* bar) {
+        const int row_hi = (it * 2) * p.w_rows + p.w_row_off, row_lo = row_hi + p.w_rows;
         if constexpr (PAIR) {
-          const uint32_t bar = ptx::mapa(ptx::smem_u32(bres_bar), 0);
-          ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)(k_iters * S::kBTileBytes));
-          for (int it = 0; it < k_iters; ++it) {
-            unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
-            ptx::tma_load_2d_pair(dst, &tm_w, bar, 0, (it * 2) * p.w_rows + w_row0);
-            ptx::tma_load_2d_pair(dst + kBRows * kBK * 2, &tm_w, bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
+          const uint32_t cbar = ptx::mapa(ptx::smem_u32(bar), 0);
+          if constexpr (STACK) {
+            // stacked operand [W_hi; W_lo]: the leader holds W_hi, the peer W_lo; then each its half of W_hi
+            const int r0 = rank ? row_lo : row_hi;
+            ptx::tma_load_2d_pair(dst, &tm_w, cbar, 0, r0);
+            ptx::tma_load_2d_pair(dst + kBRows * kBK * 2, &tm_w, cbar, 0, r0 + kBRows);
+            ptx::tma_load_2d_pair(dst + 2 * kBRows * kBK * 2, &tm_w, cbar, 0, row_hi + (int)rank * kBRows);
+          } else {
+            ptx::tma_load_2d_pair(dst, &tm_w, cbar, 0, row_hi + (int)rank * kBRows);
+            ptx::tma_load_2d_pair(dst + kBRows * kBK * 2, &tm_w, cbar, 0, row_lo + (int)rank * kBRows);
           }
         } else {
-          ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
-          for (int it = 0; it < k_iters; ++it) {
-            unsigned char* dst = b_ring + (size_t)it * S::kBTileBytes;
-            ptx::tma_load_2d(dst, &tm_w, bres_bar, 0, (it * 2) * p.w_rows + w_row0);
-            ptx::tma_load_2d(dst + kBRows * kBK * 2, &tm_w, bres_bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
-          }
+          ptx::tma_load_2d(dst, &tm_w, bar, 0, row_hi);                       // [W_hi; W_lo], also the stacked operand
+          ptx::tma_load_2d(dst + kBRows * kBK * 2, &tm_w, bar, 0, row_lo);
         }
+      };
+      auto expect_b = [&](uint64_t* bar, uint32_t bytes) {
+        if constexpr (PAIR) ptx::mbar_arrive_expect_tx_cluster(ptx::mapa(ptx::smem_u32(bar), 0), bytes);
+        else ptx::mbar_arrive_expect_tx(bar, bytes);
+      };
+      if (resident && ptx::elect_one_sync()) {
+        expect_b(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
+        for (int it = 0; it < k_iters; ++it) load_b(b_ring + (size_t)it * S::kBTileBytes, it, bres_bar);
       }
       __syncwarp();
       ptx::griddep_wait();                        // activations come from the preceding kernel
@@ -246,17 +262,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 const int it = (tap0 + j) * p.kblocks + kb;          // [tap][kb][plane][rows] blocks of 64-wide rows
                 ptx::mbar_wait(&b_empty[bs], bph ^ 1);
                 if (ptx::elect_one_sync()) {
-                  unsigned char* sb = b_ring + (size_t)bs * S::kBTileBytes;
-                  if constexpr (PAIR) {
-                    const uint32_t bar = ptx::mapa(ptx::smem_u32(&b_full[bs]), 0);
-                    ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)S::kBTileBytes);
-                    ptx::tma_load_2d_pair(sb, &tm_w, bar, 0, (it * 2) * p.w_rows + w_row0);
-                    ptx::tma_load_2d_pair(sb + kBRows * kBK * 2, &tm_w, bar, 0, (it * 2 + 1) * p.w_rows + w_row0);
-                  } else {
-                    ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)S::kBTileBytes);
-                    ptx::tma_load_2d(sb, &tm_w, &b_full[bs], 0, (it * 2) * p.w_rows + w_row0);
-                    ptx::tma_load_2d(sb + kBRows * kBK * 2, &tm_w, &b_full[bs], 0, (it * 2 + 1) * p.w_rows + w_row0);
-                  }
+                  expect_b(&b_full[bs], (uint32_t)S::kBTileBytes);
+                  load_b(b_ring + (size_t)bs * S::kBTileBytes, it, &b_full[bs]);
                 }
                 __syncwarp();
                 if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
@@ -270,6 +277,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
     {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 256 : 128, BN);
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(PAIR ? 256 : 128, 2 * BN);     // stacked operand
       // plain (CTA-scope) waits also for the barriers the peer signals: the data they guard moves through the async
       // proxy (TMA -> UMMA) or TMEM (ordered by the tcgen05 fences); a cluster-scope acquire on the MMA-issuing thread
       // costs ~0.7 us per wait and starves the tensor pipe
@@ -307,19 +315,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 ptx::tc_fence_after();
                 b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
               }
-              const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_hi + kBRows * kBK * 2);
+              // stacked: db_hi = [W_hi; W_lo] (2*BN rows over the CTA / the pair), db_lo = W_hi alone
+              const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi);
+              const uint64_t db_lo = ptx::umma_desc_k_sw128(b_hi + (STACK ? (PAIR ? 2 * kBRows * kBK * 2 : 0) : kBRows * kBK * 2));
               if (ptx::elect_one_sync()) {
               for (int sub = 0; sub < (PAIR ? 1 : p.n_sub); ++sub) {
                 // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
                 const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
                 const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_hi + p.a_plane_bytes);
-                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + sub) * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + sub) * S::kAccCols);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                   const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
-                  mma(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
-                  mma(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-                  mma(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                  if constexpr (STACK) {
+                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc2, accumulate | (uint32_t)k);   // A_hi x [W_hi; W_lo]
+                    mma(tmem_d, da_lo + koff, db_lo + koff, idesc, 1);                          // A_lo x W_hi
+                  } else {
+                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
+                    mma(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+                    mma(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+                  }
                 }
               }
               if (!resident) commit(&b_empty[bs]);                // frees the weight slot when these MMAs have read it
@@ -394,12 +409,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         float hacc[kMaxHeadOut];
 #pragma unroll
         for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
-        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * BN + col0);
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * S::kAccCols + col0);
 #pragma unroll 1
         for (int j = 0; j < kColsPerWarp / 16; ++j) {
           const int cb = col0 + j * 16;              // first output channel of this chunk
           uint32_t acc[16];
           ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+          uint32_t acc2[16];                         // stacked operand: the hi x lo products live BN columns further
+          if constexpr (STACK) ptx::tmem_ld_32x32b_x16(tmem_acc + BN + j * 16, acc2);
           uint32_t rhw[8], rlw[8];                   // residual of this chunk (requested one chunk ago)
           if (p.res_mode) {
 #pragma unroll
@@ -414,10 +431,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
             for (int g = 0; g < 4; ++g) {          // bias: per-image slice (conv bias already folded in) or the conv's own
               const float4 b4 = *reinterpret_cast<const float4*>(bsrc + cb + 4 * g);
-              v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
-              v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
-              v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
-              v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
+              if constexpr (STACK) {
+                v[4 * g + 0] = (__uint_as_float(acc[4 * g + 0]) + __uint_as_float(acc2[4 * g + 0])) + b4.x;
+                v[4 * g + 1] = (__uint_as_float(acc[4 * g + 1]) + __uint_as_float(acc2[4 * g + 1])) + b4.y;
+                v[4 * g + 2] = (__uint_as_float(acc[4 * g + 2]) + __uint_as_float(acc2[4 * g + 2])) + b4.z;
+                v[4 * g + 3] = (__uint_as_float(acc[4 * g + 3]) + __uint_as_float(acc2[4 * g + 3])) + b4.w;
+              } else {
+                v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + b4.x;
+                v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + b4.y;
+                v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + b4.z;
+                v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + b4.w;
+              }
             }
             if (p.res_mode) {
 #pragma unroll
@@ -579,6 +603,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const int want_group = want_group_raw & 3;
   static const bool use_pdl = [] { const char* e = getenv("STP3_CONV_PDL"); return !e || atoi(e) != 0; }();
   const bool stream_weights = (want_group_raw & 4) != 0;    // +4: keep the weights in the ring even if they would fit
+  const bool stack = (want_group_raw & 8) != 0 && d->bn == 64;   // +8: stacked [W_hi; W_lo] operand (bn = 64 only)
   // taps that can share one activation load: runs (<= 4) of consecutive taps with the same (dt, dx) and dy advancing
   // by the stride
   ConvParams p;
@@ -684,9 +709,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     p.vec256 = (y_hi && d->out_cstride % 16 == 0 && p.out_coff % 16 == 0 && al32(y_hi) && al32(y_lo) ? 1 : 0) |
                (d->res_mode && d->res_cstride % 16 == 0 && p.res_coff % 16 == 0 && al32(res_hi) && al32(res_lo) ? 2 : 0);
-#define STP3_LAUNCH_CONV(BN_, PAIR_)                                                                              \
+#define STP3_LAUNCH_CONV(BN_, PAIR_, STACK_)                                                                      \
     do {                                                                                                          \
-      using SM = ConvSmem<BN_, PAIR_>;                                                                            \
+      using SM = ConvSmem<BN_, PAIR_, STACK_>;                                                                    \
       const size_t avail = smem_cap - 1024 - SM::tail_bytes();                                                    \
       const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                    \
       /* small weight tensors stay resident in smem next to >= 2 activation stages */                            \
@@ -708,7 +733,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       if (nb > kMaxBStages) nb = kMaxBStages;                                                                     \
       p.na_stages = na; p.nb_stages = nb; p.b_resident = res ? 1 : 0;                                             \
       const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * SM::kBTileBytes) + SM::tail_bytes(); \
-      auto kern = conv_igemm_kernel<BN_, PAIR_>;                                                                  \
+      auto kern = conv_igemm_kernel<BN_, PAIR_, STACK_>;                                                          \
       STP3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));       \
       cudaLaunchConfig_t cfg = {};                                                                                \
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads);                                                \
@@ -733,8 +758,12 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       }                                                                                                           \
       STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));                                        \
     } while (0)
-    if (bn_launch == 64) { if (pair) STP3_LAUNCH_CONV(64, true); else STP3_LAUNCH_CONV(64, false); }
-    else { if (pair) STP3_LAUNCH_CONV(128, true); else STP3_LAUNCH_CONV(128, false); }
+    if (bn_launch == 64) {
+      if (stack) { if (pair) STP3_LAUNCH_CONV(64, true, true); else STP3_LAUNCH_CONV(64, false, true); }
+      else { if (pair) STP3_LAUNCH_CONV(64, true, false); else STP3_LAUNCH_CONV(64, false, false); }
+    } else {
+      if (pair) STP3_LAUNCH_CONV(128, true, false); else STP3_LAUNCH_CONV(128, false, false);
+    }
 #undef STP3_LAUNCH_CONV
     STP3_CUDA_OK(cudaGetLastError());
   }

@@ -138,12 +138,14 @@ _TUNE_PAIR = _os.environ.get("STP3_CONV_PAIR", "1") != "0"
 TUNE_LOG = []      # (description, {config: ms}) for reports
 
 
-def _tune(key, desc, launch, groupable, ntaps=1):
+def _tune(key, desc, launch, groupable, ntaps=1, bn=0):
     cands = [(1, 1), (2, 1)] + ([(1, 3), (2, 3)] if groupable else [])
     if _TUNE_PAIR:
         cands += [(3, 1)] + ([(3, 3)] if groupable else [])
     if ntaps > 1:       # weights streamed through the ring instead of resident: more activation stages in flight
         cands += [(ns, g + 4) for ns, g in cands if ns != 1]
+    if bn == 64:        # stacked [W_hi; W_lo] operand: two MMAs per product instead of three
+        cands += [(ns, g + 8) for ns, g in cands]
     times = {}
     for ns, g in cands:
         launch(ns, g)                                   # warm (descriptor / attribute setup)
@@ -167,7 +169,8 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
     img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table()).
-    tune = (n_sub, group) forces a tiling (n_sub 3 = CTA pair) instead of the autotuned one."""
+    tune = (n_sub, group) forces a tiling (n_sub 3 = CTA pair; group +4 = streamed weights, +8 = stacked hi/lo weight
+    operand) instead of the autotuned one."""
     B, T_total, H, W, cs = x.hi.shape
     t0, T = frames if frames is not None else (0, T_total)      # process frames [t0, t0+T) of every sample
     Ho, Wo = out_hw if out_hw is not None else ((H + pc.stride - 1) // pc.stride, (W + pc.stride - 1) // pc.stride)
@@ -226,7 +229,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         groupable = any(taps[i + 1][0] == taps[i][0] and taps[i + 1][2] == taps[i][2] and
                         taps[i + 1][1] == taps[i][1] + pc.stride for i in range(len(taps) - 1))
         desc = f"{len(taps)}tap cin{pc.cin_p} bn{pc.bn} s{pc.stride} {B * T}x{Ho}x{Wo}"
-        cfg = _tune(key, desc, launch, groupable, len(taps))
+        cfg = _tune(key, desc, launch, groupable, len(taps), pc.bn)
     launch(*(cfg or (0, 0)))
     return out
 

@@ -111,6 +111,29 @@ def test_stride2_tap_groups(tune, k, hw):
     check(from_hl(y, 0, 64), F.relu(ref_conv2d(x, w, b, stride=2)))
 
 
+@pytest.mark.parametrize("tune", [(1, 9), (2, 9), (1, 11), (2, 11), (3, 9), (3, 11), (3, 15), (2, 13)])
+@pytest.mark.parametrize("cin,cout,k,hw,T", [
+    (64, 64, 3, (40, 37), 2),         # resident weights
+    (128, 35, 3, (24, 24), 3),        # two K blocks, padded Cout
+    (64, 64, 1, (50, 50), 1),         # 1x1
+])
+def test_stacked_weight_operand(tune, cin, cout, k, hw, T):
+    """bn = 64 layers may evaluate a product as A_hi x [W_hi; W_lo] (N = 128) + A_lo x W_hi (N = 64) -- two MMAs
+    instead of three; the epilogue adds the two accumulator halves.  Same three product terms, same result."""
+    if (tune[1] & 3) == 3 and k != 3:
+        pytest.skip("taps are not groupable")
+    H, W = hw
+    x = rnd(1, T, cin, H, W, seed=61)
+    w = rnd(cout, cin, k, k, seed=62, scale=(cin * k * k) ** -0.5)
+    b = rnd(cout, seed=63)
+    res = rnd(1, T, cout, H, W, seed=64)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    assert pc.bn == 64
+    y = dense.conv(to_hl(x), pc, relu=True, residual=to_hl(res), tune=tune)
+    torch.cuda.synchronize()
+    check(from_hl(y, 0, cout), F.relu(ref_conv2d(x, w, b) + res.double()))
+
+
 def test_pair_tiling_with_fused_epilogues():
     """CTA-pair tiling with residual, per-image bias and odd image sizes (the peer CTA's rows fall off the image)."""
     B, T, C, H, W = 2, 2, 64, 9, 21

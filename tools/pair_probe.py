@@ -23,7 +23,9 @@ def run(name, cin, cout, k, dil=1, stride=1, hw=(H, W)):
     w = torch.randn(cout, cin, k, k, device=dev) * 0.05
     pc = dense.pack_conv(w, torch.zeros(cout, device=dev), dilation=dil, stride=stride)
     groupable = k == 3 and dil == 1 and stride == 1
-    cfgs = [(1, 1), (2, 1), (3, 1)] + ([(1, 3), (2, 3), (3, 3)] if groupable else [])
+    cfgs = [(2, 1), (3, 1)] + ([(2, 3), (3, 3)] if groupable else [])
+    if cout <= 64:
+        cfgs += [(ns, g + 8) for ns, g in cfgs]
     out = "  ".join(f"{c}: {t(lambda: dense.conv(x, pc, relu=True, tune=c)):7.1f}us" for c in cfgs)
     print(f"{name:28s} {out}", flush=True)
 
