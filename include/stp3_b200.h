@@ -129,6 +129,8 @@ typedef struct stp3_conv_desc {
   int tune_group;        /* 0 = automatic; 1 = never share an activation load between the dy taps of a 3x3; 3 = share;
                             +4 = stream the weights through the smem ring even if they would fit (more activation stages);
                             +8 = (bn 64) one stacked [W_hi; W_lo] operand: 2 MMAs per product instead of 3 */
+  int n_cols;            /* output columns that carry weights (0 = bn): rows [n_cols, bn) of every weight block and the
+                            bias are zero padding, so the kernel neither loads nor multiplies them (bn <= 128) */
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:

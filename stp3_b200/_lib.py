@@ -24,7 +24,8 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("T_total", _I), ("t0", _I), ("in_cstride", _I), ("cin_off", _I), ("cin", _I),
                 ("Ho", _I), ("Wo", _I), ("stride", _I), ("ntaps", _I), ("taps", (ctypes.c_byte * 3) * 49),
                 ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("n_store", _I), ("relu", _I), ("res_mode", _I),
-                ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I), ("tune_n_sub", _I), ("tune_group", _I)]
+                ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I), ("tune_n_sub", _I), ("tune_group", _I),
+                ("n_cols", _I)]
 
 
 class ConvHead(ctypes.Structure):

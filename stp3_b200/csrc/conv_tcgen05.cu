@@ -56,6 +56,10 @@ struct ConvParams {
   int n_groups, gmax;
   unsigned char gstart[kMaxTaps], gsize[kMaxTaps];
   int a_plane_bytes;        // bytes of one activation plane of a stage = box_h * 16 px * 128 B
+  int n_mma;                // output columns the MMAs compute (multiple of 16, <= BN): columns beyond the convolution's
+                            // real Cout have zero weights and bias, so they are neither loaded nor multiplied
+  int b_rows;               // weight rows of one plane part held by this CTA: n_mma, or n_mma / 2 in a pair
+  int b_tile_bytes;         // shared-memory bytes of one K step's weights (2 parts; 3 for a stacked pair)
   int w_rows;               // rows per (tap, kb, plane) block of the packed weight tensor (the convolution's padded Cout)
   int w_row_off;            // first row of this launch inside that block (a 256-channel conv runs as two launches)
   signed char tap[kMaxTaps][4];   // (dt, dy, dx): input coordinate = output coordinate * stride + d
@@ -135,7 +139,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using S = ConvSmem<BN, PAIR, STACK>;
   static_assert(!STACK || BN == 64, "stacked weight operand: BN = 64 only (TMEM columns)");
-  constexpr int kBRows = S::kBRows;
+  const int kBRows = p.b_rows;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;              // 0 = leader
   const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a pair walks together)
   const int n_cta = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -148,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   const int a_stage_bytes = 2 * p.a_plane_bytes;
   unsigned char* a_ring = smem;
   unsigned char* b_ring = a_ring + (size_t)p.na_stages * a_stage_bytes;            // ring, or the resident weights
-  float* s_bias = reinterpret_cast<float*>(b_ring + (size_t)(resident ? k_iters : p.nb_stages) * S::kBTileBytes);
+  float* s_bias = reinterpret_cast<float*>(b_ring + (size_t)(resident ? k_iters : p.nb_stages) * p.b_tile_bytes);
   float* s_head = s_bias + BN;                    // [kMaxHeadOut][BN]
   float* s_hx = s_head + kMaxHeadOut * BN;        // [kMaxHeadOut][128] head partials handed between column halves
   float* s_wb = s_hx + kMaxHeadOut * 128;         // [kEpiWarps][64] per-image bias slice of each epilogue warp
@@ -223,8 +227,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         else ptx::mbar_arrive_expect_tx(bar, bytes);
       };
       if (resident && ptx::elect_one_sync()) {
-        expect_b(bres_bar, (uint32_t)(k_iters * S::kBTileBytes));
-        for (int it = 0; it < k_iters; ++it) load_b(b_ring + (size_t)it * S::kBTileBytes, it, bres_bar);
+        expect_b(bres_bar, (uint32_t)(k_iters * p.b_tile_bytes));
+        for (int it = 0; it < k_iters; ++it) load_b(b_ring + (size_t)it * p.b_tile_bytes, it, bres_bar);
       }
       __syncwarp();
       ptx::griddep_wait();                        // activations come from the preceding kernel
@@ -262,8 +266,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 const int it = (tap0 + j) * p.kblocks + kb;          // [tap][kb][plane][rows] blocks of 64-wide rows
                 ptx::mbar_wait(&b_empty[bs], bph ^ 1);
                 if (ptx::elect_one_sync()) {
-                  expect_b(&b_full[bs], (uint32_t)S::kBTileBytes);
-                  load_b(b_ring + (size_t)bs * S::kBTileBytes, it, &b_full[bs]);
+                  expect_b(&b_full[bs], (uint32_t)p.b_tile_bytes);
+                  load_b(b_ring + (size_t)bs * p.b_tile_bytes, it, &b_full[bs]);
                 }
                 __syncwarp();
                 if (++bs == p.nb_stages) { bs = 0; bph ^= 1; }
@@ -276,8 +280,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (whole warp walks the loops; one elected lane issues) =====================
     {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 256 : 128, BN);
-      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(PAIR ? 256 : 128, 2 * BN);     // stacked operand
+      const uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 256 : 128, p.n_mma);
+      const uint32_t idesc2 = ptx::umma_idesc_bf16(PAIR ? 256 : 128, 2 * p.n_mma);     // stacked operand
       // plain (CTA-scope) waits also for the barriers the peer signals: the data they guard moves through the async
       // proxy (TMA -> UMMA) or TMEM (ordered by the tcgen05 fences); a cluster-scope acquire on the MMA-issuing thread
       // costs ~0.7 us per wait and starves the tensor pipe
@@ -309,11 +313,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               const int it = (tap0 + j) * p.kblocks + kb;
               uint32_t b_hi;
               if (resident) {
-                b_hi = ptx::smem_u32(b_ring + (size_t)it * S::kBTileBytes);
+                b_hi = ptx::smem_u32(b_ring + (size_t)it * p.b_tile_bytes);
               } else {
                 wait_full(&b_full[bs], bph);
                 ptx::tc_fence_after();
-                b_hi = ptx::smem_u32(b_ring + (size_t)bs * S::kBTileBytes);
+                b_hi = ptx::smem_u32(b_ring + (size_t)bs * p.b_tile_bytes);
               }
               // stacked: db_hi = [W_hi; W_lo] (2*BN rows over the CTA / the pair), db_lo = W_hi alone
               const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi);
@@ -414,9 +418,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         for (int j = 0; j < kColsPerWarp / 16; ++j) {
           const int cb = col0 + j * 16;              // first output channel of this chunk
           uint32_t acc[16];
-          ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
-          uint32_t acc2[16];                         // stacked operand: the hi x lo products live BN columns further
-          if constexpr (STACK) ptx::tmem_ld_32x32b_x16(tmem_acc + BN + j * 16, acc2);
+          uint32_t acc2[16];                         // stacked operand: the hi x lo products live n_mma columns further
+          const bool computed = cb < p.n_mma;        // columns beyond n_mma: zero weights, never multiplied
+          if (computed) {
+            ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+            if constexpr (STACK) ptx::tmem_ld_32x32b_x16(tmem_acc + p.n_mma + j * 16, acc2);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc[i] = 0u; acc2[i] = 0u; }
+          }
           uint32_t rhw[8], rlw[8];                   // residual of this chunk (requested one chunk ago)
           if (p.res_mode) {
 #pragma unroll
@@ -649,10 +659,12 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   }
   const int kblocks = d->cin / kBK;
   const int bn_launch = d->bn == 256 ? 128 : d->bn;     // 256 output channels run as two 128-column launches
+  // the MMAs cover only the columns that carry weights (n_cols, rounded up to the UMMA granularity of 16)
+  const int n_mma = d->bn <= 128 && d->n_cols > 0 && d->n_cols < d->bn ? ((d->n_cols + 15) / 16) * 16 : bn_launch;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)kBK, (cuuint64_t)d->ntaps * kblocks * 2 * d->bn};
     const cuuint64_t strides[1] = {(cuuint64_t)kBK * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(pair ? bn_launch / 2 : bn_launch)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(pair ? n_mma / 2 : n_mma)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -667,7 +679,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0 && d->taps[i][1] == 0 && d->taps[i][2] == 0) p.skip_t = 1;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
-  p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn;
+  p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn; p.n_mma = n_mma;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
   p.relu = d->relu; p.res_mode = d->res_mode;
   p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
@@ -712,8 +724,10 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
 #define STP3_LAUNCH_CONV(BN_, PAIR_, STACK_)                                                                      \
     do {                                                                                                          \
       using SM = ConvSmem<BN_, PAIR_, STACK_>;                                                                    \
+      p.b_rows = PAIR_ ? n_mma / 2 : n_mma;                                                                       \
+      p.b_tile_bytes = (STACK_ && PAIR_ ? 3 : 2) * p.b_rows * kBK * 2;                                            \
       const size_t avail = smem_cap - 1024 - SM::tail_bytes();                                                    \
-      const size_t wbytes = (size_t)k_iters * SM::kBTileBytes;                                                    \
+      const size_t wbytes = (size_t)k_iters * (size_t)p.b_tile_bytes;                                                    \
       /* small weight tensors stay resident in smem next to >= 2 activation stages */                            \
       const bool res = !stream_weights && wbytes + 2 * a_stage <= avail;                                          \
       int na, nb;                                                                                                 \
@@ -722,17 +736,17 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       } else {                                                                                                    \
         /* as many activation stages as fit beside max(2, group) weight slots, then fill up with weight slots */  \
         const int nb_min = group > 2 ? group : 2;                                                                 \
-        na = (int)((avail - (size_t)nb_min * SM::kBTileBytes) / a_stage);                                         \
+        na = (int)((avail - (size_t)nb_min * (size_t)p.b_tile_bytes) / a_stage);                                         \
         if (na < 2) na = 2;                                                                                       \
         if (na > kMaxAStages) na = kMaxAStages;                                                                   \
-        if ((size_t)na * a_stage + 2 * SM::kBTileBytes > avail)                                                   \
+        if ((size_t)na * a_stage + 2 * (size_t)p.b_tile_bytes > avail)                                                   \
           return set_error(STP3_EUNSUPPORTED, "convolution does not fit in shared memory");                       \
-        nb = (int)((avail - (size_t)na * a_stage) / SM::kBTileBytes);                                             \
+        nb = (int)((avail - (size_t)na * a_stage) / (size_t)p.b_tile_bytes);                                             \
       }                                                                                                           \
       if (na > kMaxAStages) na = kMaxAStages;                                                                     \
       if (nb > kMaxBStages) nb = kMaxBStages;                                                                     \
       p.na_stages = na; p.nb_stages = nb; p.b_resident = res ? 1 : 0;                                             \
-      const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * SM::kBTileBytes) + SM::tail_bytes(); \
+      const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * (size_t)p.b_tile_bytes) + SM::tail_bytes(); \
       auto kern = conv_igemm_kernel<BN_, PAIR_, STACK_>;                                                          \
       STP3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));       \
       cudaLaunchConfig_t cfg = {};                                                                                \

@@ -18,7 +18,7 @@ int set_error(int code, const char* fmt, ...) {
 
 }  // namespace stp3
 
-extern "C" int stp3_abi_version(void) { return 1; }
+extern "C" int stp3_abi_version(void) { return 2; }
 
 extern "C" const char* stp3_build_info(void) {
   return "stp3_b200 abi 1; sm_100a; nvcc " __DATE__ " " __TIME__;

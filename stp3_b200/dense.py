@@ -183,6 +183,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
     for i, (dt, dy, dx) in enumerate(pc.taps):
         d.taps[i][0], d.taps[i][1], d.taps[i][2] = dt, dy, dx
     d.bn = pc.bn
+    d.n_cols = pc.cout              # weight rows / bias entries beyond cout are zero padding
     if out is None and out_f32 is None and store:
         out = HL.empty(B, T, Ho, Wo, pc.cout, x.hi.device, cp=pc.bn)
     hd = None
