@@ -373,7 +373,10 @@ def main():
         ls_ms = stage_ms.get("lift_splat", ms_per_step)
         roof_ls = {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
                    "achieved": alg / (ls_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                   "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"], "traffic": None,
+                   "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
+                   # dram__bytes_read+write of scatter (106.5 MB) + finalize (159.4 MB) for this workload at B=4,
+                   # profiles/r01_ncu_liftsplat_v6_summary.txt (one ncu --set full capture; scales with B)
+                   "traffic": int(265.9e6 * b / 4) if perceive else None,
                    "algorithmic_bytes_per_step": alg, "ms": ls_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -398,7 +401,10 @@ def main():
             line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN> family (temporal model + decoder, 45 launches/step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
-                                "traffic": None, "algorithmic_flops_per_step": flops, "ms": dense_ms,
+                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v6_pair_summary.txt
+                                # (temporal model + first decoder convs, B=4): 4273 MB read + 2206 MB written
+                                "traffic": int(6479e6 * b / 4), "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
+                                "algorithmic_flops_per_step": flops, "ms": dense_ms,
                                 "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
             line["roofline_lift_splat"] = roof_ls
         else:
