@@ -100,8 +100,10 @@ class TemporalBlock(PackedModule):
         cin, half, cout, nc = self.in_channels, self.half_channels, self.out_channels, self.n_const
         cs = cin - nc                                  # spatial input channels
         o = _round8(half)
-        assert half <= 64 and 3 * o <= 128 and cout <= 256, "channel counts beyond the reference's configurations"
-        P = {"o": o, "cs": cs}
+        assert half <= 128 and cout <= 256, "at most 256 input / output channels per block"
+        hp = dense.pad_to(half)                        # channel window of one mid path (multiple of 64)
+        ap = dense.pad_to(3 * o)                       # channels of the concat tensor the aggregation conv reads
+        P = {"o": o, "cs": cs, "hp": hp, "ap": ap}
         flat = lambda w: w.reshape(w.shape[0], w.shape[1])
         p0, p1, p2 = self.convolution_paths
         # fused entry convolutions of paths 0 and 1 (N = 128: path 0 at rows 0.., path 1 at rows 64..)
@@ -109,8 +111,9 @@ class TemporalBlock(PackedModule):
         w1, b1 = dense.fold_bn(p1[0].conv.weight, p1[0].norm)
         # path 0 lives at channel 0 of `mid`; path 1 right behind it when both fit one 64-channel K block (block 2 of
         # the reference: 32 + 32), else in the next block (block 1: 35 + 35)
-        m1 = half if 2 * half <= 64 else 64
-        nmid = 64 if m1 == half else 128
+        shared = 2 * half <= 64                        # both mid paths fit one 64-channel K block
+        m1 = half if shared else hp
+        nmid = 64 if shared else 2 * hp
         P["m1"], P["nmid"] = m1, nmid
         wa = torch.zeros(nmid, cin, device=w0.device)
         ba = torch.zeros(nmid, device=w0.device)
@@ -118,15 +121,15 @@ class TemporalBlock(PackedModule):
         ba[:half], ba[m1:m1 + half] = b0, b1
         P["a1"] = dense.pack_conv(wa[:, :cs].reshape(nmid, cs, 1, 1).contiguous(), ba, bn=nmid)
         w2, b2 = dense.fold_bn(p2.conv.weight, p2.norm)
-        P["a2"] = dense.pack_conv(flat(w2)[:, :cs].reshape(half, cs, 1, 1).contiguous(), b2, bn=64)
+        P["a2"] = dense.pack_conv(flat(w2)[:, :cs].reshape(half, cs, 1, 1).contiguous(), b2)
         wt, bt = dense.fold_bn(p0[1].conv.weight, p0[1].norm)          # (half, half, 2, 3, 3)
-        P["b"] = dense.pack_conv(wt, bt, cin_p=64, bn=64)
+        P["b"] = dense.pack_conv(wt, bt, cin_p=hp)
         ws, bs = dense.fold_bn(p1[1].conv.weight, p1[1].norm)          # (half, half, 1, 3, 3)
-        P["c"] = dense.pack_conv(ws, bs, cin_p=64, bn=64, in_layout=[(0, half, m1 % 64)])
+        P["c"] = dense.pack_conv(ws, bs, cin_p=hp, in_layout=[(0, half, m1 % 64)])
         wg, bg = dense.fold_bn(self.aggregation[0].conv.weight, self.aggregation[0].norm)
         wg = flat(wg)
         P["agg"] = dense.pack_conv(wg[:, :3 * half].reshape(cout, 3 * half, 1, 1).contiguous(), bg,
-                                   in_layout=[(0, half, 0), (half, half, o), (2 * half, half, 2 * o)], cin_p=128)
+                                   in_layout=[(0, half, 0), (half, half, o), (2 * half, half, 2 * o)], cin_p=ap)
         if self.use_pyramid_pooling:
             wp, bp = dense.fold_bn(self.pyramid_pooling.features[0].conv_bn_relu.conv.weight,
                                    self.pyramid_pooling.features[0].conv_bn_relu.norm)
@@ -164,13 +167,14 @@ class TemporalBlock(PackedModule):
 
         mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
         m1 = P["m1"]
-        agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=128)
+        ap = P["ap"]
+        agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=ap)
         dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
         dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
         # the last path also fills the padding channels of the concat tensor: its own padded output columns are exact
         # zeros (zero weights and bias), so storing 128 - 2*o of them saves a separate fill
-        tail = min(64, 128 - 2 * o)
-        if 2 * o + tail < 128:                                   # narrow blocks (half < 25): fill what a2 cannot reach
+        tail = min(P["a2"].bn, ap - 2 * o)
+        if 2 * o + tail < ap:                                    # fill what a2's padded columns cannot reach
             agg.hi[..., 2 * o + tail:].zero_(); agg.lo[..., 2 * o + tail:].zero_()
         dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=tail, relu=True,
                    img_bias=const_bias(P.get("a2_c"), P["a2"]))

@@ -58,7 +58,13 @@ def test_upsampling_add():
     close(y, ref)
 
 
-@pytest.mark.parametrize("cin,cout", [(70, 64), (64, 64)])
+@pytest.mark.parametrize("cin,cout", [
+    (70, 64), (64, 64),       # the two blocks of the perceive configuration
+    (134, 64),                # stress configuration (C = 128 + 6 ego-motion channels): 67-channel paths, 216-channel concat
+    (20, 24),                 # narrow: both mid paths share one 64-channel block
+    (128, 128),               # identity skip with 64-channel paths
+    (200, 96),                # 100-channel paths
+])
 def test_temporal_block(cin, cout):
     H, W = 20, 28
     with torch.no_grad():

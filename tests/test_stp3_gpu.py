@@ -29,15 +29,22 @@ class FakeTrunk(torch.nn.Module):
         return r3, r4
 
 
-def small_cfg():
-    return get_cfg({"LIFT": {"X_BOUND": [-8.0, 8.0, 0.5], "Y_BOUND": [-8.0, 8.0, 0.5], "D_BOUND": [2.0, 10.0, 1.0]},
-                    "IMAGE": {"FINAL_DIM": (32, 48)}})
+def small_cfg(extra=None):
+    d = {"LIFT": {"X_BOUND": [-8.0, 8.0, 0.5], "Y_BOUND": [-8.0, 8.0, 0.5], "D_BOUND": [2.0, 10.0, 1.0]},
+         "IMAGE": {"FINAL_DIM": (32, 48)}}
+    for k, v in (extra or {}).items():
+        if isinstance(v, dict):
+            d.setdefault(k, {}).update(v)
+        else:
+            d[k] = v
+    return get_cfg(d)
 
 
-def test_forward_features_matches_composed_oracle():
-    cfg = small_cfg()
+@pytest.mark.parametrize("C,S", [(64, 3), (128, 5)])      # perceive shape; stress shape (BASELINE configs[4]: C=128, S=5)
+def test_forward_features_matches_composed_oracle(C, S):
+    cfg = small_cfg({"TIME_RECEPTIVE_FIELD": S, "MODEL": {"ENCODER": {"OUT_CHANNELS": C}}} if (C, S) != (64, 3) else None)
     lcfg = syn.LiftSplatConfig(x_bound=(-8.0, 8.0, 0.5), y_bound=(-8.0, 8.0, 0.5), d_bound=(2.0, 10.0, 1.0),
-                               final_dim=(32, 48), out_channels=64, n_cameras=2, receptive_field=3)
+                               final_dim=(32, 48), out_channels=C, n_cameras=2, receptive_field=S)
     inp = syn.lift_inputs(lcfg, 2, seed=4, random_pose=True)
     with torch.no_grad():
         model = TD.init_exact(STP3(cfg, backbone=FakeTrunk()), seed=7).eval()
@@ -58,7 +65,7 @@ def test_forward_features_matches_composed_oracle():
         x = torch.from_numpy(bev)                                            # (B,S,64,X,Y) fp64
         ego = inp["future_egomotion"].double()
         ego = torch.cat([torch.zeros_like(ego[:, :1]), ego[:, :-1]], 1)      # stp3.py:148-151
-        x = torch.cat([x, ego.view(2, 3, 6, 1, 1).expand(2, 3, 6, *x.shape[-2:])], dim=2)
+        x = torch.cat([x, ego.view(2, S, 6, 1, 1).expand(2, S, 6, *x.shape[-2:])], dim=2)
         states = TD.temporal_model(x, ref_model.temporal_model)
         ref = TD.decoder(states, ref_model.decoder)
     assert out["depth_prediction"].shape == inp["depth_logits"].shape and out["cam_front"] is None
