@@ -40,7 +40,11 @@ WORKLOADS = {
                 "excluded on both arms)",
     "lift_splat": "lift_splat: 6 cam x 3 t x (28x60x48 frustum) -> 200x200x64 BEV, ego-warp + discount "
                   "(BASELINE configs[2] lift-splat stage)",
+    "stress": "stress: 6 cam x 5 t x (28x60x96 frustum), C=128 -> lift-splat -> 4 temporal blocks + DeepLab head -> BEV "
+              "decoder heads, 400x400 BEV (BASELINE configs[4]; a robustness / maximum-size run, not the headline metric)",
 }
+# the whole perception path runs for these workloads (the others stop after the lift-splat)
+PERCEPTION = ("perceive", "stress")
 
 
 def algorithmic_bytes_lift_splat(cfg, batch):
@@ -118,11 +122,16 @@ def make_problem(cfg, batch, seed):
                 off=G.bev_offset(start, res))
 
 
-def build_model(device=None):
+def build_model(device=None, lcfg=None):
     """Random-init (seeded, machine-independent) perception model; the trunk is not needed (inputs enter after it)."""
     from stp3_b200.config import get_cfg
     from stp3_b200.models.stp3 import STP3
-    cfg = get_cfg()
+    over = None
+    if lcfg is not None and lcfg is not syn.CONFIGS["perceive"]:
+        over = {"LIFT": {"X_BOUND": list(lcfg.x_bound), "Y_BOUND": list(lcfg.y_bound), "Z_BOUND": list(lcfg.z_bound),
+                         "D_BOUND": list(lcfg.d_bound)},
+                "TIME_RECEPTIVE_FIELD": lcfg.receptive_field, "MODEL": {"ENCODER": {"OUT_CHANNELS": lcfg.out_channels}}}
+    cfg = get_cfg(over)
     with torch.no_grad():
         model = STP3(cfg, backbone=torch.nn.Identity())
         geo = {k: getattr(model, k).detach().clone() for k in ("frustum", "bev_resolution", "bev_start_position", "bev_dimension")}
@@ -176,7 +185,7 @@ def pick_threads(cfg, prob):
 
 def time_reference(workload, cfg, steps, warmup):
     prob = make_problem(cfg, 1, seed=0)
-    model = build_model() if workload == "perceive" else None
+    model = build_model(lcfg=cfg) if workload in PERCEPTION else None
     threads = pick_threads(cfg, prob)
     for _ in range(warmup):
         reference_step(workload, cfg, prob, model)
@@ -222,7 +231,7 @@ def main():
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the resident timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
-    cfg = syn.CONFIGS["perceive"]
+    cfg = syn.CONFIGS["stress" if args.workload == "stress" else "perceive"]
 
     if args.impl == "reference":
         run_reference_arm(args, cfg)
@@ -244,7 +253,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     W, K, b = max(args.warmup, 3), args.steps, args.batch
-    perceive = args.workload == "perceive"
+    perceive = args.workload in PERCEPTION
 
     prob = make_problem(cfg, b, seed=rank)          # every rank works on its own shard of the global batch
     inp = prob["inp"]
@@ -255,15 +264,15 @@ def main():
     d_mats = [m.to(dev) for m in host_mats]
     X, Y = cfg.bev_xy
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    model = build_model(dev) if perceive else None
+    model = build_model(dev, cfg) if perceive else None
     graphed = None
     if perceive and not args.no_graph:
         from stp3_b200.models.stp3 import GraphedPerception
         graphed = GraphedPerception(model, b, cfg.n_cameras, dev)
         graphed(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])   # fill the static inputs
     if perceive:
-        host_out = {"segmentation": torch.empty((b, 3, 2, X, Y)).pin_memory(),
-                    "pedestrian": torch.empty((b, 3, 2, X, Y)).pin_memory(),
+        host_out = {"segmentation": torch.empty((b, cfg.receptive_field, 2, X, Y)).pin_memory(),
+                    "pedestrian": torch.empty((b, cfg.receptive_field, 2, X, Y)).pin_memory(),
                     "hdmap": torch.empty((b, 4, X, Y)).pin_memory()}
     else:
         out = torch.empty((b, cfg.receptive_field, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
@@ -376,7 +385,7 @@ def main():
                    "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
                    # dram__bytes_read+write of scatter (106.5 MB) + finalize (159.4 MB) for this workload at B=4,
                    # profiles/r01_ncu_liftsplat_v6_summary.txt (one ncu --set full capture; scales with B)
-                   "traffic": int(265.9e6 * b / 4) if perceive else None,
+                   "traffic": int(265.9e6 * b / 4) if args.workload == "perceive" else None,
                    "algorithmic_bytes_per_step": alg, "ms": ls_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -394,16 +403,18 @@ def main():
         }
         if perceive:
             dense_ms = stage_ms.get("temporal_model", 0.0) + stage_ms.get("decoder", 0.0)
-            flops = (GFLOP_TEMPORAL + GFLOP_DECODER) * 1e9 * b
-            ach = flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else None
+            # the flop count was taken on the reference modules for the perceive configuration only
+            flops = (GFLOP_TEMPORAL + GFLOP_DECODER) * 1e9 * b if args.workload == "perceive" else None
+            ach = flops / (dense_ms * 1e-3) / 1e12 if flops and dense_ms > 0 else None
             line["stage_ms"] = stage_ms
-            line["gpu_launches"] = 2 * K * LAUNCHES_PER_PERCEIVE_STEP
+            # every extra temporal block (stress: 4 instead of 2) adds 5 convs + 3 small kernels
+            line["gpu_launches"] = 2 * K * (LAUNCHES_PER_PERCEIVE_STEP + 8 * max(0, cfg.receptive_field - 3))
             line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN> family (temporal model + decoder, 45 launches/step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
                                 # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v6_pair_summary.txt
                                 # (temporal model + first decoder convs, B=4): 4273 MB read + 2206 MB written
-                                "traffic": int(6479e6 * b / 4), "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
+                                "traffic": int(6479e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
                                 "algorithmic_flops_per_step": flops, "ms": dense_ms,
                                 "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
             line["roofline_lift_splat"] = roof_ls
