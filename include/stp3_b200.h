@@ -165,16 +165,18 @@ int stp3_hilo_to_f32(const void* hi, const void* lo, int n_img, int H, int W, in
 /* sums[img][c] = sum over the H*W pixels (fp32, (n_img, cstride)); cstride <= 1024 */
 int stp3_spatial_sum(const void* hi, const void* lo, int n_img, int HW, int cstride, float* sums, void* stream);
 /* Spatially constant branches folded to a per-image bias of the consuming 1x1 convolution:
- *   m = sums * inv_hw (temporal != 0: averaged with the previous frame of the same sample when it exists --
- *       AvgPool3d((2,H,W), padding (1,0,0), count_include_pad=False), temporal.py:397-415)
- *   v = relu(W1 m + b1)  (R);   out[img][co] (+)= sum_r W2[co][r] v[r]
+ *   m[c] = sums[c] * inv_hw for the C - n_const spatial channels, const_vals[img][c - (C - n_const)] for the trailing
+ *       n_const spatially constant ones (their mean is the value); temporal != 0: averaged with the previous frame of
+ *       the same sample when it exists -- AvgPool3d((2,H,W), padding (1,0,0), count_include_pad=False), temporal.py:397-415
+ *   v = relu(W1 m + b1)  (R);   out[img][co] = (accumulate ? out[img][co] : bias ? bias[co] : 0) + sum_r W2[co][r] v[r]
  * Replaces PyramidSpatioTemporalPooling (temporal.py:375-423) and ASPPPooling (convolutions.py:227-239). */
 int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int T, int C, float inv_hw, int temporal,
-                   const float* W1, const float* b1, int R, const float* W2, int CO, float* out, int co_stride,
-                   int accumulate, void* stream);
-/* y[n][co] (+)= sum_ci W[co][ci] x[n][ci]: the 6 broadcast ego-motion channels of stp3.py:145-152 as a bias */
-int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, float* y, int co_stride, int accumulate,
-                      void* stream);
+                   const float* const_vals, int n_const, const float* W1, const float* b1, int R, const float* W2, int CO,
+                   const float* bias, float* out, int co_stride, int accumulate, void* stream);
+/* y[n][co] = (accumulate ? y[n][co] : bias ? bias[co] : 0) + sum_ci W[co][ci] x[n][ci]: the 6 broadcast ego-motion
+ * channels of stp3.py:145-152 as a per-image bias */
+int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, const float* bias, float* y, int co_stride,
+                      int accumulate, void* stream);
 /* y[..., y_coff:y_coff+C] = bilinear_x2(x[..., :C]) (+ skip[..., s_coff:s_coff+C] when skip is given); x is
  * (n_img,h,w,.), skip and y are (n_img,2h,2w,.).  UpsamplingAdd tail (convolutions.py:204-215) and the upsample +
  * concat of UpsamplingConcat (convolutions.py:183-201). */

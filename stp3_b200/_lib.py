@@ -43,8 +43,8 @@ SIGNATURES = {
     "stp3_f32_to_hilo": (_I, [_V, _I, _I, _I, _I, _I, _I, _V, _V, _V]),
     "stp3_hilo_to_f32": (_I, [_V, _V, _I, _I, _I, _I, _I, _I, _V, _V]),
     "stp3_spatial_sum": (_I, [_V, _V, _I, _I, _I, _V, _V]),
-    "stp3_pool_bias": (_I, [_V, _I, _I, _I, _I, _F, _I, _V, _V, _I, _V, _I, _V, _I, _I, _V]),
-    "stp3_small_linear": (_I, [_V, _V, _I, _I, _I, _V, _I, _I, _V]),
+    "stp3_pool_bias": (_I, [_V, _I, _I, _I, _I, _F, _I, _V, _I, _V, _V, _I, _V, _I, _V, _V, _I, _I, _V]),
+    "stp3_small_linear": (_I, [_V, _V, _I, _I, _I, _V, _V, _I, _I, _V]),
     "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _V]),
     "stp3_lift_splat_frames_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I,
                                         _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _V, _V]),

@@ -96,19 +96,24 @@ __global__ void spatial_sum_kernel(const __nv_bfloat16* __restrict__ hi, const _
 //   out[img][co] (+)= sum_r W2[co][r] v[r]     (its slice of the consuming 1x1 convolution, folded BN scale inside)
 // one block per image
 __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride, int T, int C, float inv_hw,
-                                 int temporal, const float* __restrict__ W1, const float* __restrict__ b1, int R,
-                                 const float* __restrict__ W2, int CO, float* __restrict__ out, int co_stride,
-                                 int accumulate) {
+                                 int temporal, const float* __restrict__ cvals, int n_const,
+                                 const float* __restrict__ W1, const float* __restrict__ b1, int R,
+                                 const float* __restrict__ W2, int CO, const float* __restrict__ bias,
+                                 float* __restrict__ out, int co_stride, int accumulate) {
   extern __shared__ float sm[];
   float* m = sm;          // [C]
   float* v = sm + C;      // [R]
   const int img = blockIdx.x;
   const int t = img % T;
+  const int cs = C - n_const;       // channels [cs, C) are spatially constant: their per-frame mean is the value itself
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = sums[(size_t)img * sums_stride + c];
+    auto frame_mean = [&](int i) {
+      return c < cs ? sums[(size_t)i * sums_stride + c] * inv_hw : cvals[(size_t)i * n_const + (c - cs)];
+    };
+    float s = frame_mean(img);
     float cnt = 1.f;
-    if (temporal && t > 0) { s += sums[(size_t)(img - 1) * sums_stride + c]; cnt = 2.f; }
-    m[c] = s * inv_hw / cnt;
+    if (temporal && t > 0) { s += frame_mean(img - 1); cnt = 2.f; }
+    m[c] = s / cnt;
   }
   __syncthreads();
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -121,19 +126,20 @@ __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride
     float a = 0.f;
     for (int r = 0; r < R; ++r) a = fmaf(W2[(size_t)co * R + r], v[r], a);
     float* dst = out + (size_t)img * co_stride + co;
-    *dst = accumulate ? *dst + a : a;
+    *dst = (accumulate ? *dst : (bias ? bias[co] : 0.f)) + a;
   }
 }
 
 // y[n][co] (+)= sum_ci W[co][ci] x[n][ci]     (ego-motion channels folded into a per-image bias, stp3.py:145-152)
 __global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, int ci, int co,
-                                    float* __restrict__ y, int co_stride, int accumulate) {
+                                    const float* __restrict__ bias, float* __restrict__ y, int co_stride,
+                                    int accumulate) {
   const int n = blockIdx.x;
   for (int o = threadIdx.x; o < co; o += blockDim.x) {
     float a = 0.f;
     for (int i = 0; i < ci; ++i) a = fmaf(W[(size_t)o * ci + i], x[(size_t)n * ci + i], a);
     float* dst = y + (size_t)n * co_stride + o;
-    *dst = accumulate ? *dst + a : a;
+    *dst = (accumulate ? *dst : (bias ? bias[o] : 0.f)) + a;
   }
 }
 
@@ -239,20 +245,22 @@ extern "C" int stp3_spatial_sum(const void* hi, const void* lo, int n_img, int H
 }
 
 extern "C" int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int T, int C, float inv_hw, int temporal,
-                              const float* W1, const float* b1, int R, const float* W2, int CO, float* out,
-                              int co_stride, int accumulate, void* stream) {
-  STP3_CHECK_ARG(sums && W1 && b1 && W2 && out && n_img > 0 && T > 0 && C > 0 && R > 0 && CO > 0 && C <= sums_stride &&
-                 CO <= co_stride, "stp3_pool_bias: bad argument");
+                              const float* const_vals, int n_const,
+                              const float* W1, const float* b1, int R, const float* W2, int CO, const float* bias,
+                              float* out, int co_stride, int accumulate, void* stream) {
+  STP3_CHECK_ARG(sums && W1 && b1 && W2 && out && n_img > 0 && T > 0 && C > 0 && R > 0 && CO > 0 && n_const >= 0 &&
+                 n_const < C && C - n_const <= sums_stride && CO <= co_stride && (n_const == 0 || const_vals),
+                 "stp3_pool_bias: bad argument");
   pool_bias_kernel<<<n_img, 128, (size_t)(C + R) * sizeof(float), (cudaStream_t)stream>>>(
-      sums, sums_stride, T, C, inv_hw, temporal, W1, b1, R, W2, CO, out, co_stride, accumulate);
+      sums, sums_stride, T, C, inv_hw, temporal, const_vals, n_const, W1, b1, R, W2, CO, bias, out, co_stride, accumulate);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }
 
-extern "C" int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, float* y, int co_stride,
-                                 int accumulate, void* stream) {
+extern "C" int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, const float* bias, float* y,
+                                 int co_stride, int accumulate, void* stream) {
   STP3_CHECK_ARG(x && W && y && n > 0 && ci > 0 && co > 0 && co <= co_stride, "stp3_small_linear: bad argument");
-  small_linear_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(x, W, ci, co, y, co_stride, accumulate);
+  small_linear_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(x, W, ci, co, bias, y, co_stride, accumulate);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
 }

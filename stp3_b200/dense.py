@@ -287,30 +287,38 @@ def spatial_sum(x: HL) -> torch.Tensor:
 
 
 def pool_bias(sums: torch.Tensor, T: int, C: int, hw: int, temporal: bool, W1, b1, W2, out: torch.Tensor,
-              accumulate: bool):
-    """out[img, :CO] (+)= W2 relu(W1 mean + b1): a spatially constant branch as a per-image bias (see header)."""
+              accumulate: bool, const: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
+    """out[img, :CO] = (out | bias | 0) + W2 relu(W1 mean + b1): a spatially constant branch as a per-image bias (see
+    header).  const (n_img, n_const): values of the trailing spatially constant input channels (not part of sums)."""
     n_img = sums.shape[0]
     R, CO = W1.shape[0], W2.shape[0]
-    assert W1.shape == (R, C) and W2.shape == (CO, R) and out.shape[0] == n_img
-    for t in (sums, W1, b1, W2, out):
+    nc = 0 if const is None else const.shape[1]
+    assert W1.shape == (R, C) and W2.shape == (CO, R) and out.shape[0] == n_img and C - nc <= sums.shape[1]
+    for t in (sums, W1, b1, W2, out) + ((const,) if nc else ()) + ((bias,) if bias is not None else ()):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    assert bias is None or bias.numel() >= CO
     with torch.cuda.device(sums.device):
         code = _lib.lib().stp3_pool_bias(sums.data_ptr(), sums.shape[1], n_img, T, C, 1.0 / hw, int(temporal),
-                                         W1.data_ptr(), b1.data_ptr(), R, W2.data_ptr(), CO, out.data_ptr(),
+                                         const.data_ptr() if nc else None, nc,
+                                         W1.data_ptr(), b1.data_ptr(), R, W2.data_ptr(), CO,
+                                         bias.data_ptr() if bias is not None else None, out.data_ptr(),
                                          out.shape[1], int(accumulate), _stream(sums.device))
     _lib.check(code, "stp3_pool_bias")
 
 
-def small_linear(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor, accumulate: bool):
-    """out[n, :co] (+)= W x[n]."""
+def small_linear(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor, accumulate: bool,
+                 bias: Optional[torch.Tensor] = None):
+    """out[n, :co] = (out | bias | 0) + W x[n]."""
     n, ci = x.shape
     co = W.shape[0]
     assert W.shape == (co, ci) and out.shape[0] == n
-    for t in (x, W, out):
+    for t in (x, W, out) + ((bias,) if bias is not None else ()):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    assert bias is None or bias.numel() >= co
     with torch.cuda.device(x.device):
-        code = _lib.lib().stp3_small_linear(x.data_ptr(), W.data_ptr(), n, ci, co, out.data_ptr(), out.shape[1],
-                                            int(accumulate), _stream(x.device))
+        code = _lib.lib().stp3_small_linear(x.data_ptr(), W.data_ptr(), n, ci, co,
+                                            bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                            out.shape[1], int(accumulate), _stream(x.device))
     _lib.check(code, "stp3_small_linear")
 
 

@@ -115,8 +115,9 @@ class DeepLabHead(nn.Sequential, PackedModule):
         for i in range(nb):
             dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
         sums = dense.spatial_sum(x)
-        pbias = dense.bias_table(P["proj"], B * T)
-        dense.pool_bias(sums, T, self.in_channels, H * W, False, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, True)
+        pbias = torch.empty((B * T, P["proj"].bn), dtype=torch.float32, device=x.hi.device)
+        dense.pool_bias(sums, T, self.in_channels, H * W, False, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
+                        bias=P["proj"].bias)
         y = dense.conv(cat, P["proj"], relu=True, img_bias=pbias)       # Dropout(0.5) is the identity in eval mode
         y = dense.conv(y, P["conv3"], relu=True)
         return dense.conv(y, P["cls"], out=out)

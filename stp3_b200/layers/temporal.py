@@ -105,6 +105,11 @@ class TemporalBlock(PackedModule):
         ap = dense.pad_to(3 * o)                       # channels of the concat tensor the aggregation conv reads
         P = {"o": o, "cs": cs, "hp": hp, "ap": ap}
         flat = lambda w: w.reshape(w.shape[0], w.shape[1])
+
+        def pad_rows(w, rows):                     # zero rows for the padded output columns: a bias table is written whole
+            out = torch.zeros(rows, w.shape[1], device=w.device)
+            out[:w.shape[0]] = w
+            return out
         p0, p1, p2 = self.convolution_paths
         # fused entry convolutions of paths 0 and 1 (N = 128: path 0 at rows 0.., path 1 at rows 64..)
         w0, b0 = dense.fold_bn(p0[0].conv.weight, p0[0].norm)
@@ -134,14 +139,14 @@ class TemporalBlock(PackedModule):
             wp, bp = dense.fold_bn(self.pyramid_pooling.features[0].conv_bn_relu.conv.weight,
                                    self.pyramid_pooling.features[0].conv_bn_relu.norm)
             P["pool_w1"], P["pool_b1"] = flat(wp).contiguous(), bp.contiguous()
-            P["pool_w2"] = wg[:, 3 * half:].contiguous()
+            P["pool_w2"] = pad_rows(wg[:, 3 * half:], P["agg"].bn)
         if self.projection is not None:
             wj, bj = dense.fold_bn(self.projection[0].weight, self.projection[1])
             P["proj"] = dense.pack_conv(flat(wj)[:, :cs].reshape(cout, cs, 1, 1).contiguous(), bj)
-            P["proj_c"] = flat(wj)[:, cs:].contiguous()
+            P["proj_c"] = pad_rows(flat(wj)[:, cs:], P["proj"].bn)
         if nc:
             P["a1_c"] = wa[:, cs:].contiguous()
-            P["a2_c"] = flat(w2)[:, cs:].contiguous()
+            P["a2_c"] = pad_rows(flat(w2)[:, cs:], P["a2"].bn)
         return P
 
     def forward_hl(self, x: dense.HL, const: Optional[torch.Tensor] = None,
@@ -158,11 +163,11 @@ class TemporalBlock(PackedModule):
         cin, half, cout, o, cs = self.in_channels, self.half_channels, self.out_channels, P["o"], P["cs"]
         n_img = B * T
 
-        def const_bias(wc, pc):
+        def const_bias(wc, pc):                    # per-image bias = conv bias + W[:, constant channels] . const
             if not nc:
                 return None
-            b = dense.bias_table(pc, n_img)
-            dense.small_linear(const, wc, b, True)
+            b = torch.empty((n_img, pc.bn), dtype=torch.float32, device=dev)
+            dense.small_linear(const, wc, b, False, bias=pc.bias)
             return b
 
         mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
@@ -184,12 +189,9 @@ class TemporalBlock(PackedModule):
             assert (ph, pw) == (H, W), "pyramid pooling must span the whole map (as configured by TemporalModel)"
             if sums is None:
                 sums = dense.spatial_sum(x)
-            full = torch.empty((n_img, cin), dtype=torch.float32, device=dev)
-            full[:, :cs] = sums[:, :cs]
-            if nc:
-                full[:, cs:] = const * float(H * W)
-            pbias = dense.bias_table(P["agg"], n_img)
-            dense.pool_bias(full, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, True)
+            pbias = torch.empty((n_img, P["agg"].bn), dtype=torch.float32, device=dev)
+            dense.pool_bias(sums, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
+                            const=const if nc else None, bias=P["agg"].bias)
         if self.projection is not None:
             res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"]))
         else:
