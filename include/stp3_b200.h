@@ -131,6 +131,12 @@ typedef struct stp3_conv_desc {
                             +8 = (bn 64) one stacked [W_hi; W_lo] operand: 2 MMAs per product instead of 3 */
   int n_cols;            /* output columns that carry weights (0 = bn): rows [n_cols, bn) of every weight block and the
                             bias are zero padding, so the kernel neither loads nor multiplies them (bn <= 128) */
+  /* optional (bn = 64): col_sums[img][c] = sum over the output pixels of the activated output (fp32, (B*T, 64)) -- the
+     spatial sums the next block's pooling branches need, produced by the epilogue instead of a separate pass.
+     col_sums_scratch: stp3_conv_col_sums_scratch_bytes(B*T, 64) bytes of device scratch. */
+  float* col_sums;
+  float* col_sums_scratch;
+  size_t col_sums_scratch_bytes;
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:
@@ -148,6 +154,8 @@ typedef struct stp3_conv_head {
   int sigmoid_mask;
 } stp3_conv_head;
 
+/* bytes of device scratch stp3_conv_desc.col_sums needs for n_img images */
+size_t stp3_conv_col_sums_scratch_bytes(int n_img, int bn);
 int stp3_conv_fwd(const stp3_conv_desc* desc, const void* x_hi, const void* x_lo, const void* w, const float* bias,
                   const float* img_bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
                   float* y_f32, const stp3_conv_head* head /* may be NULL */, void* stream);

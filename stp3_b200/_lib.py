@@ -25,7 +25,7 @@ class ConvDesc(ctypes.Structure):
                 ("Ho", _I), ("Wo", _I), ("stride", _I), ("ntaps", _I), ("taps", (ctypes.c_byte * 3) * 49),
                 ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("n_store", _I), ("relu", _I), ("res_mode", _I),
                 ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I), ("tune_n_sub", _I), ("tune_group", _I),
-                ("n_cols", _I)]
+                ("n_cols", _I), ("col_sums", _V), ("col_sums_scratch", _V), ("col_sums_scratch_bytes", _SZ)]
 
 
 class ConvHead(ctypes.Structure):
@@ -36,6 +36,7 @@ class ConvHead(ctypes.Structure):
 
 SIGNATURES = {
     "stp3_abi_version": (_I, []),
+    "stp3_conv_col_sums_scratch_bytes": (_SZ, [_I, _I]),
     "stp3_build_info": (ctypes.c_char_p, []),
     "stp3_last_error": (ctypes.c_char_p, []),
     "stp3_lift_splat_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),

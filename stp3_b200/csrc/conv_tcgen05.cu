@@ -87,6 +87,10 @@ struct ConvParams {
   float* head_out[8];       // plane of output k for image 0 (fp32, (Ho, Wo))
   long long head_img_stride[8];   // elements between consecutive images for output k
   int head_sigmoid_mask;    // bit k: sigmoid on output k
+  // per-image column sums of the activated output (the consumer's pooling branches need sum over H*W): every epilogue
+  // warp keeps running sums of its pixels in registers and writes one partial row per (CTA, lane quarter, image) --
+  // plain stores, fixed order: deterministic.  BN = 64 only.  sum_part: [gridDim.x][4][n_img][BN], zeroed by the host.
+  float* sum_part;
 };
 
 // STACK (BN = 64 only): the hi and lo weight planes of a K step form ONE B operand of 2*BN rows, so a product is two
@@ -366,10 +370,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int col0 = half * kColsPerWarp;
     const int r = q * 32 + lane;                 // row of the sub-tile = output pixel
     int buf = 0; uint32_t acc_phase = 0;
+    constexpr bool kSums = BN == 64;              // column sums need kColsPerWarp (= 32) accumulators per thread
+    float sacc[kSums ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (kSums ? 32 : 1); ++i) sacc[i] = 0.f;
+    int sum_img = -1;
+    auto flush_sums = [&](int img_) {             // 32 lanes x 32 columns -> lane l holds column col0 + l (halving butterfly)
+      if constexpr (kSums) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < off) {
+              const float send = upper ? sacc[i] : sacc[i + off];
+              const float keep = upper ? sacc[i + off] : sacc[i];
+              sacc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        }
+        p.sum_part[(((size_t)blockIdx.x * 4 + q) * p.n_img + img_) * BN + col0 + lane] = sacc[0];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
+      }
+    };
     ptx::griddep_wait();                          // residual / per-image bias reads and every global write come after
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
       const int oy_t = (rem / p.tiles_x) * tile_h + (int)rank * kSubH, ox = (rem % p.tiles_x) * kTileW + (r & 15);
+      if (kSums && p.sum_part && img != sum_img) {      // tiles come in image order: hand the finished image over
+        if (sum_img >= 0) flush_sums(sum_img);
+        sum_img = img;
+      }
       // latency hiding: the residual of the first chunk and this warp's slice of the per-image bias are requested
       // before waiting for the accumulator; every later residual chunk is requested one chunk ahead
       const int n_sub_eff = PAIR ? 1 : p.n_sub;
@@ -501,6 +533,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 }
               }
             }
+            if constexpr (kSums) {
+              if (p.sum_part) {
+                if (j == 0) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) sacc[i] += v[i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) sacc[16 + i] += v[i];
+                }
+              }
+            }
             if (p.head_ko) {
 #pragma unroll
               for (int k = 0; k < kMaxHeadOut; ++k) {
@@ -545,6 +588,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       }
       if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
+    if (kSums && p.sum_part && sum_img >= 0) flush_sums(sum_img);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -552,6 +596,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   if (warp == 1) {
     if constexpr (PAIR) ptx::tmem_dealloc_pair<S::kTmemCols>(tmem_base);
     else ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+}
+
+// col_sums[img][c] = sum over the (CTA, lane quarter) partial rows, in a fixed order: block (bn, 16) -- 16 slices of the
+// partial rows, independent loads issued in batches, then a fixed-order sum of the slices through shared memory
+__global__ void col_sum_reduce_kernel(const float* __restrict__ part, int n_part, int n_img, int bn,
+                                      float* __restrict__ out) {
+  __shared__ float sm[16][64];
+  const int img = blockIdx.x, c = threadIdx.x, sl = threadIdx.y;
+  const int per = (n_part + 15) / 16;
+  const int k0 = sl * per, k1 = min(n_part, k0 + per);
+  float a = 0.f;
+  for (int kb = k0; kb < k1; kb += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = kb + i < k1 ? part[((size_t)(kb + i) * n_img + img) * bn + c] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += v[i];
+  }
+  sm[sl][c] = a;
+  __syncthreads();
+  if (sl == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += sm[i][c];
+    out[(size_t)img * bn + c] = t;
   }
 }
 
@@ -575,6 +645,20 @@ static PFN_tmapEncodeTiled encode_fn() {
 }  // namespace stp3
 
 using namespace stp3;
+
+static int conv_num_sms() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+extern "C" size_t stp3_conv_col_sums_scratch_bytes(int n_img, int bn) {
+  return (size_t)conv_num_sms() * 4 * (size_t)(n_img > 0 ? n_img : 0) * (size_t)(bn > 0 ? bn : 0) * sizeof(float);
+}
 
 extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const void* x_lo, const void* w,
                              const float* bias, const float* img_bias, const void* res_hi, const void* res_lo,
@@ -698,16 +782,22 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const long long nblk = (long long)p.n_img * p.tiles_x * p.tiles_y;
   STP3_CHECK_ARG(nblk > 0 && nblk < (1ll << 31), "grid too large");
   p.n_tiles = (int)nblk;
-  static const int num_sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
+  const int num_sms = conv_num_sms();
   unsigned grid = (unsigned)(nblk < num_sms ? nblk : num_sms);           // persistent: one CTA per SM
   if (pair) grid = 2u * (unsigned)(nblk < num_sms / 2 ? nblk : num_sms / 2);
   const size_t smem_cap = 227 * 1024;
   const size_t a_stage = 2 * (size_t)p.a_plane_bytes;
+
+  int launched_grid = (int)grid;
+  p.sum_part = nullptr;
+  if (d->col_sums) {
+    STP3_CHECK_ARG(d->bn == 64, "col_sums: 64-column convolutions only");
+    STP3_CHECK_ARG(d->col_sums_scratch && d->col_sums_scratch_bytes >= stp3_conv_col_sums_scratch_bytes(p.n_img, 64),
+                   "col_sums: scratch buffer missing or smaller than stp3_conv_col_sums_scratch_bytes()");
+    p.sum_part = static_cast<float*>(d->col_sums_scratch);
+    // CTAs that never see an image leave its partial rows untouched: start from zeros
+    STP3_CUDA_OK(cudaMemsetAsync(p.sum_part, 0, (size_t)grid * 4 * p.n_img * 64 * sizeof(float), stream));
+  }
 
   for (int part = 0; part * bn_launch < d->bn; ++part) {
     const int coff = part * bn_launch;
@@ -770,6 +860,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
         attr[1].val.clusterDim.x = PAIR_ ? 2 : 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;     \
         cfg.numAttrs = PAIR_ ? 2 : 1;                                                                             \
       }                                                                                                           \
+      launched_grid = (int)cfg.gridDim.x;                                                                         \
       STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, tm_w, p));                                        \
     } while (0)
     if (bn_launch == 64) {
@@ -779,6 +870,11 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       if (pair) STP3_LAUNCH_CONV(128, true, false); else STP3_LAUNCH_CONV(128, false, false);
     }
 #undef STP3_LAUNCH_CONV
+    STP3_CUDA_OK(cudaGetLastError());
+  }
+  if (p.sum_part) {
+    col_sum_reduce_kernel<<<p.n_img, dim3(64, 16), 0, stream>>>(p.sum_part, launched_grid * 4, p.n_img, 64,
+                                                      static_cast<float*>(d->col_sums));
     STP3_CUDA_OK(cudaGetLastError());
   }
   return STP3_OK;

@@ -166,9 +166,11 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          img_bias: Optional[torch.Tensor] = None, residual: Optional[HL] = None, res_coff: int = 0,
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
          out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
-         head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None) -> Optional[HL]:
+         head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None,
+         col_sums: Optional[torch.Tensor] = None) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
     img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table()).
+    col_sums (B*T, 64) fp32 (bn = 64 layers): receives the per-image sums over pixels of the activated output.
     tune = (n_sub, group) forces a tiling (n_sub 3 = CTA pair; group +4 = streamed weights, +8 = stacked hi/lo weight
     operand) instead of the autotuned one."""
     B, T_total, H, W, cs = x.hi.shape
@@ -207,6 +209,12 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         d.res_cstride, d.res_coff = residual.hi.shape[-1], res_coff
         assert residual.hi.shape[:4] == (B, T, Ho, Wo)
     d.n_valid, d.sigmoid = n_valid, int(sigmoid)
+    scratch = None
+    if col_sums is not None:
+        assert pc.bn == 64 and col_sums.shape == (B * T, 64) and col_sums.dtype == torch.float32 and col_sums.is_contiguous()
+        nbytes = _lib.lib().stp3_conv_col_sums_scratch_bytes(B * T, 64)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.hi.device)
+        d.col_sums, d.col_sums_scratch, d.col_sums_scratch_bytes = col_sums.data_ptr(), scratch.data_ptr(), nbytes
     if img_bias is not None:
         assert img_bias.shape == (B * T, pc.bn) and img_bias.dtype == torch.float32 and img_bias.is_contiguous()
     dev = x.hi.device

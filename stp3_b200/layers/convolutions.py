@@ -104,8 +104,9 @@ class DeepLabHead(nn.Sequential, PackedModule):
         P["nb"] = nb
         return P
 
-    def forward_hl(self, x: dense.HL, out: Optional[dense.HL] = None) -> dense.HL:
-        """x: HL (B,T,H,W,>=Cin) -> HL with num_classes channels (every (b,t) image independently)."""
+    def forward_hl(self, x: dense.HL, out: Optional[dense.HL] = None, sums: Optional[torch.Tensor] = None) -> dense.HL:
+        """x: HL (B,T,H,W,>=Cin) -> HL with num_classes channels (every (b,t) image independently); sums: optional
+        (B*T, >= Cin) spatial sums of x when the producer already has them."""
         self._require_eval()
         P = self.packed()
         B, T, H, W, _ = x.hi.shape
@@ -114,7 +115,8 @@ class DeepLabHead(nn.Sequential, PackedModule):
         cat = dense.HL.empty(B, T, H, W, nb * h, dev, cp=nb * h)
         for i in range(nb):
             dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
-        sums = dense.spatial_sum(x)
+        if sums is None:
+            sums = dense.spatial_sum(x)
         pbias = torch.empty((B * T, P["proj"].bn), dtype=torch.float32, device=x.hi.device)
         dense.pool_bias(sums, T, self.in_channels, H * W, False, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
                         bias=P["proj"].bias)

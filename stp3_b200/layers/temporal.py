@@ -150,10 +150,11 @@ class TemporalBlock(PackedModule):
         return P
 
     def forward_hl(self, x: dense.HL, const: Optional[torch.Tensor] = None,
-                   sums: Optional[torch.Tensor] = None) -> dense.HL:
+                   sums: Optional[torch.Tensor] = None, out_sums: Optional[torch.Tensor] = None) -> dense.HL:
         """x: HL (B,T,H,W,.) holding the spatial input channels; const: (B*T, n_const) fp32 values of the spatially
         constant trailing channels (requires self.n_const == const.shape[1]); sums: optional precomputed per-image
-        spatial sums of x (B*T, >= spatial channels), e.g. emitted by the lift-splat finalize kernel."""
+        spatial sums of x (B*T, >= spatial channels), e.g. emitted by the lift-splat finalize kernel; out_sums (B*T, 64):
+        receives the spatial sums of the block's output from the aggregation conv's epilogue (64-channel blocks)."""
         self._require_eval()
         nc = 0 if const is None else const.shape[1]
         assert nc == self.n_const, "set TemporalBlock.n_const to the number of spatially constant input channels"
@@ -197,7 +198,7 @@ class TemporalBlock(PackedModule):
         else:
             assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
             res = x
-        return dense.conv(agg, P["agg"], relu=True, img_bias=pbias, residual=res, res_after_act=True)
+        return dense.conv(agg, P["agg"], relu=True, img_bias=pbias, residual=res, res_after_act=True, col_sums=out_sums)
 
     def forward(self, *inputs):
         """x (B, C, T, H, W) fp32 -> (B, Cout, T, H, W) fp32, like the reference module."""

@@ -27,9 +27,16 @@ class TemporalModel(nn.Module):
         self.model = nn.Sequential(*blocks)
 
     def forward_hl(self, x: dense.HL, const=None, sums=None) -> dense.HL:
+        n_img = x.hi.shape[0] * x.hi.shape[1]
         for i, block in enumerate(self.model):
-            x = block.forward_hl(x, const if i == 0 else None, sums if i == 0 else None)
-        return self.final_conv.forward_hl(x)
+            # a 64-channel block hands the spatial sums of its output (the next block's pyramid pooling / the head's
+            # global-pool branch need them) over from its aggregation conv's epilogue
+            nxt = None
+            if block.out_channels <= 64:
+                nxt = torch.empty((n_img, 64), dtype=torch.float32, device=x.hi.device)
+            x = block.forward_hl(x, const if i == 0 else None, sums, out_sums=nxt)
+            sums = nxt
+        return self.final_conv.forward_hl(x, sums=sums)
 
     def forward(self, x):
         """x (B, S, C, H, W) fp32 -> (B, S, Cout, H, W) fp32."""

@@ -134,6 +134,31 @@ def test_stacked_weight_operand(tune, cin, cout, k, hw, T):
     check(from_hl(y, 0, cout), F.relu(ref_conv2d(x, w, b) + res.double()))
 
 
+@pytest.mark.parametrize("tune", [(1, 1), (2, 3), (3, 3), (3, 11), (2, 9)])
+def test_column_sums_from_the_epilogue(tune):
+    """col_sums: per-image sums over pixels of the activated output (what the next block's pooling branches read),
+    accumulated by the epilogue warps and reduced in a fixed order -> deterministic."""
+    B, T, C, H, W = 2, 3, 64, 37, 29
+    x = rnd(B, T, C, H, W, seed=71)
+    w = rnd(40, C, 3, 3, seed=72, scale=0.05)
+    b = rnd(40, seed=73)
+    res = rnd(B, T, 40, H, W, seed=74)
+    pc = dense.pack_conv(w.to(DEV), b.to(DEV))
+    sums = torch.full((B * T, 64), float("nan"), device=DEV)
+    y = dense.conv(to_hl(x), pc, relu=True, residual=to_hl(res), res_after_act=True, tune=tune, col_sums=sums)
+    sums2 = torch.empty_like(sums)
+    dense.conv(to_hl(x), pc, relu=True, residual=to_hl(res), res_after_act=True, tune=tune, col_sums=sums2)
+    torch.cuda.synchronize()
+    ref = F.relu(ref_conv2d(x, w, b)) + res.double()
+    check(from_hl(y, 0, 40), ref)
+    ref_sums = ref.sum(dim=(-2, -1)).view(B * T, 40)
+    got = sums.cpu().double()
+    assert torch.equal(sums, sums2), "not deterministic"
+    assert float(got[:, 40:].abs().max()) == 0.0
+    err = (got[:, :40] - ref_sums).abs().max().item()
+    assert err <= 3e-5 * ref_sums.abs().max().item() + 1e-3, (err, ref_sums.abs().max().item())
+
+
 def test_pair_tiling_with_fused_epilogues():
     """CTA-pair tiling with residual, per-image bias and odd image sizes (the peer CTA's rows fall off the image)."""
     B, T, C, H, W = 2, 2, 64, 9, 21
