@@ -383,9 +383,9 @@ def main():
         roof_ls = {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
                    "achieved": alg / (ls_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
-                   # dram__bytes_read+write of scatter (106.5 MB) + finalize (159.4 MB) for this workload at B=4,
-                   # profiles/r01_ncu_liftsplat_v6_summary.txt (one ncu --set full capture; scales with B)
-                   "traffic": int(265.9e6 * b / 4) if args.workload == "perceive" else None,
+                   # dram__bytes_read+write of scatter (105.2 MB) + finalize (154.3 MB) for this workload at B=4,
+                   # profiles/r01_ncu_liftsplat_v8_summary.txt (one ncu --set full capture; scales with B)
+                   "traffic": int(259.5e6 * b / 4) if args.workload == "perceive" else None,
                    "algorithmic_bytes_per_step": alg, "ms": ls_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -412,9 +412,9 @@ def main():
             line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN> family (temporal model + decoder, 45 launches/step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
-                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v6_pair_summary.txt
-                                # (temporal model + first decoder convs, B=4): 4273 MB read + 2206 MB written
-                                "traffic": int(6479e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
+                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v8_summary.txt
+                                # (temporal model + first decoder convs, B=4): 4248 MB read + 2223 MB written
+                                "traffic": int(6471e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
                                 "algorithmic_flops_per_step": flops, "ms": dense_ms,
                                 "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
             line["roofline_lift_splat"] = roof_ls
@@ -486,9 +486,9 @@ def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
     return out
 
 
-# kernels of this repository launched by one perceive step: lift-splat 2, temporal blocks 2x(6 conv + 2 small),
-# DeepLab head 7 conv + 2, decoder 1 + 12 + 2 ds + 3 (1x1) + 3 upsample + heads 4, layout/aux ~6
-LAUNCHES_PER_PERCEIVE_STEP = 66
+# kernels of this repository launched by one perceive step (profiles/r01_launches_perceive_v8.csv): 43 conv_igemm,
+# lift-splat scatter + finalize + pool reduce, 3 upsample, 3 pool_bias, 3 small_linear, 2 col_sum_reduce
+LAUNCHES_PER_PERCEIVE_STEP = 57
 
 
 if __name__ == "__main__":

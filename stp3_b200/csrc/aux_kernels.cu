@@ -116,17 +116,25 @@ __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride
     m[c] = s / cnt;
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    float a = b1[r];
-    for (int c = 0; c < C; ++c) a = fmaf(W1[(size_t)r * C + c], m[c], a);
-    v[r] = fmaxf(a, 0.f);
+  // one warp per output row, lanes stride over the inputs (the serial per-thread dot products were latency-bound)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nwarps) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(W1[(size_t)r * C + c], m[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) v[r] = fmaxf(a + b1[r], 0.f);
   }
   __syncthreads();
-  for (int co = threadIdx.x; co < CO; co += blockDim.x) {
+  for (int co = warp; co < CO; co += nwarps) {
     float a = 0.f;
-    for (int r = 0; r < R; ++r) a = fmaf(W2[(size_t)co * R + r], v[r], a);
-    float* dst = out + (size_t)img * co_stride + co;
-    *dst = (accumulate ? *dst : (bias ? bias[co] : 0.f)) + a;
+    for (int r = lane; r < R; r += 32) a = fmaf(W2[(size_t)co * R + r], v[r], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      float* dst = out + (size_t)img * co_stride + co;
+      *dst = (accumulate ? *dst : (bias ? bias[co] : 0.f)) + a;
+    }
   }
 }
 
@@ -251,7 +259,7 @@ extern "C" int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int
   STP3_CHECK_ARG(sums && W1 && b1 && W2 && out && n_img > 0 && T > 0 && C > 0 && R > 0 && CO > 0 && n_const >= 0 &&
                  n_const < C && C - n_const <= sums_stride && CO <= co_stride && (n_const == 0 || const_vals),
                  "stp3_pool_bias: bad argument");
-  pool_bias_kernel<<<n_img, 128, (size_t)(C + R) * sizeof(float), (cudaStream_t)stream>>>(
+  pool_bias_kernel<<<n_img, 256, (size_t)(C + R) * sizeof(float), (cudaStream_t)stream>>>(
       sums, sums_stride, T, C, inv_hw, temporal, const_vals, n_const, W1, b1, R, W2, CO, bias, out, co_stride, accumulate);
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;
