@@ -137,6 +137,12 @@ typedef struct stp3_conv_desc {
   float* col_sums;
   float* col_sums_scratch;
   size_t col_sums_scratch_bytes;
+  /* optional second destination (bn = 128, plain hi/lo outputs, n_store <= 64): output columns [64, 64 + n_store2) are
+     written to y2 (channels [out2_coff, out2_coff + n_store2)) with activation relu2, columns [0, n_store) to y with
+     `relu` -- two 64-column convolutions of the same input as ONE launch that reads the input once. */
+  void* y2_hi;
+  void* y2_lo;
+  int out2_cstride, out2_coff, n_store2, relu2;
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:

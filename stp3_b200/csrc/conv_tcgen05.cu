@@ -87,6 +87,11 @@ struct ConvParams {
   float* head_out[8];       // plane of output k for image 0 (fp32, (Ho, Wo))
   long long head_img_stride[8];   // elements between consecutive images for output k
   int head_sigmoid_mask;    // bit k: sigmoid on output k
+  // second destination (BN = 128): output columns [64, 128) go to another tensor with their own activation flag -- two
+  // 64-column convolutions that read the same input run as one launch and read it once
+  __nv_bfloat16* out2_hi;
+  __nv_bfloat16* out2_lo;
+  int out2_cstride, out2_coff, n_store2, relu2;
   // per-image column sums of the activated output (the consumer's pooling branches need sum over H*W): every epilogue
   // warp keeps running sums of its pixels in registers and writes one partial row per (CTA, lane quarter, image) --
   // plain stores, fixed order: deterministic.  BN = 64 only.  sum_part: [gridDim.x][4][n_img][BN], zeroed by the host.
@@ -369,6 +374,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     constexpr int kColsPerWarp = BN / 2;
     const int col0 = half * kColsPerWarp;
     const int r = q * 32 + lane;                 // row of the sub-tile = output pixel
+    // destination of this warp's columns (the upper column half may belong to a second tensor)
+    const bool second = BN == 128 && half == 1 && p.out2_hi != nullptr;
+    __nv_bfloat16* const d_hi = second ? p.out2_hi : p.out_hi;
+    __nv_bfloat16* const d_lo = second ? p.out2_lo : p.out_lo;
+    const int d_cstride = second ? p.out2_cstride : p.out_cstride;
+    const int d_coff = second ? p.out2_coff - 64 : p.out_coff;          // d_coff + column = channel in the destination
+    const int d_nstore = second ? 64 + p.n_store2 : p.n_store;
+    const bool d_relu = (second ? p.relu2 : p.relu) != 0;
+    const bool d_vec = ((p.vec256 >> (second ? 2 : 0)) & 1) != 0;
     int buf = 0; uint32_t acc_phase = 0;
     constexpr bool kSums = BN == 64;              // column sums need kColsPerWarp (= 32) accumulators per thread
     float sacc[kSums ? 32 : 1];
@@ -491,16 +505,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 const float r0 = __uint_as_float(rhw[e2] << 16) + __uint_as_float(rlw[e2] << 16);
                 const float r1 = __uint_as_float(rhw[e2] & 0xFFFF0000u) + __uint_as_float(rlw[e2] & 0xFFFF0000u);
                 float& a0 = v[e2 * 2], &a1 = v[e2 * 2 + 1];
-                if (p.res_mode == 1) { a0 += r0; a1 += r1; if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
-                else { if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
+                if (p.res_mode == 1) { a0 += r0; a1 += r1; if (d_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } }
+                else { if (d_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); } a0 += r0; a1 += r1; }
               }
-            } else if (p.relu) {
+            } else if (d_relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.out_hi && cb < p.n_store) {
-              __nv_bfloat16* ohp = p.out_hi + pix * p.out_cstride + p.out_coff + cb;
-              __nv_bfloat16* olp = p.out_lo + pix * p.out_cstride + p.out_coff + cb;
+            if (d_hi && cb < d_nstore) {
+              __nv_bfloat16* ohp = d_hi + pix * d_cstride + d_coff + cb;
+              __nv_bfloat16* olp = d_lo + pix * d_cstride + d_coff + cb;
               uint32_t hw[8], lw[8];
 #pragma unroll
               for (int e2 = 0; e2 < 8; ++e2) {
@@ -510,13 +524,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 hw[e2] = h;
                 lw[e2] = ptx::pack_bf16x2(r0, r1);
               }
-              if ((p.vec256 & 1) && cb + 16 <= p.n_store) {     // one full 32-byte sector per plane and lane
+              if (d_vec && cb + 16 <= d_nstore) {               // one full 32-byte sector per plane and lane
                 ptx::st_global_v8(ohp, hw);
                 ptx::st_global_v8(olp, lw);
               } else {
                 reinterpret_cast<uint4*>(ohp)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 reinterpret_cast<uint4*>(olp)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                if (cb + 8 < p.n_store) {
+                if (cb + 8 < d_nstore) {
                   reinterpret_cast<uint4*>(ohp)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                   reinterpret_cast<uint4*>(olp)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
                 }
@@ -770,6 +784,16 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   p.res_cstride = d->res_cstride;
   p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
   p.out_cstride = d->out_cstride;
+  p.out2_hi = static_cast<__nv_bfloat16*>(d->y2_hi); p.out2_lo = static_cast<__nv_bfloat16*>(d->y2_lo);
+  p.out2_cstride = d->out2_cstride; p.out2_coff = d->out2_coff; p.relu2 = d->relu2;
+  p.n_store2 = d->n_store2 > 0 ? d->n_store2 : 64;
+  if (d->y2_hi) {
+    STP3_CHECK_ARG(d->bn == 128 && d->y2_lo && y_hi && !d->res_mode && !head && !y_f32 && !d->col_sums,
+                   "second destination: 128-column convolutions with plain hi/lo outputs only");
+    STP3_CHECK_ARG(n_store <= 64 && p.n_store2 % 8 == 0 && p.n_store2 <= 64 && d->out2_cstride % 8 == 0 &&
+                   d->out2_coff % 8 == 0 && d->out2_coff + p.n_store2 <= d->out2_cstride,
+                   "second destination: channel window does not fit");
+  }
   p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
   p.img_bias_stride = d->bn;
   p.head_ko = 0; p.head_w = nullptr; p.head_b = nullptr; p.head_sigmoid_mask = 0;
@@ -810,7 +834,8 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     p.f32_coff = coff;
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     p.vec256 = (y_hi && d->out_cstride % 16 == 0 && p.out_coff % 16 == 0 && al32(y_hi) && al32(y_lo) ? 1 : 0) |
-               (d->res_mode && d->res_cstride % 16 == 0 && p.res_coff % 16 == 0 && al32(res_hi) && al32(res_lo) ? 2 : 0);
+               (d->res_mode && d->res_cstride % 16 == 0 && p.res_coff % 16 == 0 && al32(res_hi) && al32(res_lo) ? 2 : 0) |
+               (d->y2_hi && d->out2_cstride % 16 == 0 && d->out2_coff % 16 == 0 && al32(d->y2_hi) && al32(d->y2_lo) ? 4 : 0);
 #define STP3_LAUNCH_CONV(BN_, PAIR_, STACK_)                                                                      \
     do {                                                                                                          \
       using SM = ConvSmem<BN_, PAIR_, STACK_>;                                                                    \

@@ -167,9 +167,12 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          res_after_act: bool = False, out_f32: Optional[torch.Tensor] = None, n_valid: int = 0, sigmoid: bool = False,
          out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
          head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None,
-         col_sums: Optional[torch.Tensor] = None) -> Optional[HL]:
+         col_sums: Optional[torch.Tensor] = None, out2: Optional[HL] = None, out2_coff: int = 0, n_store2: int = 0,
+         relu2: bool = False) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
     img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table()).
+    out2 (bn = 128 layers, n_store <= 64): output columns [64, 64+n_store2) go to out2[..., out2_coff:...] with activation
+    relu2 -- two 64-column convolutions of the same input in one launch.
     col_sums (B*T, 64) fp32 (bn = 64 layers): receives the per-image sums over pixels of the activated output.
     tune = (n_sub, group) forces a tiling (n_sub 3 = CTA pair; group +4 = streamed weights, +8 = stacked hi/lo weight
     operand) instead of the autotuned one."""
@@ -209,6 +212,10 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         d.res_cstride, d.res_coff = residual.hi.shape[-1], res_coff
         assert residual.hi.shape[:4] == (B, T, Ho, Wo)
     d.n_valid, d.sigmoid = n_valid, int(sigmoid)
+    if out2 is not None:
+        assert pc.bn == 128 and out is not None and out2.hi.shape[:4] == (B, T, Ho, Wo)
+        d.y2_hi, d.y2_lo = out2.hi.data_ptr(), out2.lo.data_ptr()
+        d.out2_cstride, d.out2_coff, d.n_store2, d.relu2 = out2.hi.shape[-1], out2_coff, n_store2, int(relu2)
     scratch = None
     if col_sums is not None:
         assert pc.bn == 64 and col_sums.shape == (B * T, 64) and col_sums.dtype == torch.float32 and col_sums.is_contiguous()
@@ -231,7 +238,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         _lib.check(code, "stp3_conv_fwd")
 
     key = (pc.w.data_ptr(), B, T, H, W, cs, cin_off, Ho, Wo, t0, int(relu), residual is not None, out_f32 is not None,
-           hd is not None)
+           hd is not None, out2 is not None)
     cfg = tune if tune is not None else _TUNED.get(key)
     if cfg is None and _AUTOTUNE and not torch.cuda.is_current_stream_capturing():
         taps = pc.taps

@@ -147,6 +147,24 @@ class TemporalBlock(PackedModule):
         if nc:
             P["a1_c"] = wa[:, cs:].contiguous()
             P["a2_c"] = pad_rows(flat(w2)[:, cs:], P["a2"].bn)
+        # Two 64-column 1x1x1 convolutions of x as ONE 128-column launch with two destinations (x is read once):
+        #   no projection (block 2 of the reference): [paths 0+1 entry -> mid | path 2 -> concat tensor]
+        #   projection   (block 1):                    [path 2 -> concat tensor | projection -> skip tensor]
+        w2p, b2p = pad_rows(flat(w2), 64) if half <= 64 else None, None
+        if half <= 64:
+            b2p = torch.zeros(64, device=w0.device); b2p[:half] = b2
+        if self.projection is None and nmid == 64 and half <= 64:
+            wm = torch.cat([wa, w2p], 0)
+            P["a12"] = dense.pack_conv(wm[:, :cs].reshape(128, cs, 1, 1).contiguous(), torch.cat([ba, b2p]), bn=128)
+            if nc:
+                P["a12_c"] = wm[:, cs:].contiguous()
+        if self.projection is not None and half <= 64 and cout <= 64:
+            wjp = pad_rows(flat(wj), 64)
+            bjp = torch.zeros(64, device=w0.device); bjp[:cout] = bj
+            wm = torch.cat([w2p, wjp], 0)
+            P["a2p"] = dense.pack_conv(wm[:, :cs].reshape(128, cs, 1, 1).contiguous(), torch.cat([b2p, bjp]), bn=128)
+            if nc:
+                P["a2p_c"] = wm[:, cs:].contiguous()
         return P
 
     def forward_hl(self, x: dense.HL, const: Optional[torch.Tensor] = None,
@@ -171,19 +189,30 @@ class TemporalBlock(PackedModule):
             dense.small_linear(const, wc, b, False, bias=pc.bias)
             return b
 
-        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
         m1 = P["m1"]
         ap = P["ap"]
         agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=ap)
+        # the last path also fills the padding channels of the concat tensor: its own padded output columns are exact
+        # zeros (zero weights and bias), so storing up to 64 of them saves a separate fill
+        tail = min(P["a2"].bn, ap - 2 * o)
+        if 2 * o + tail < ap:                                    # fill what path 2's padded columns cannot reach
+            agg.hi[..., 2 * o + tail:].zero_(); agg.lo[..., 2 * o + tail:].zero_()
+        res = None
+        if "a12" in P:         # [mid | path 2] in one launch
+            mid = dense.HL.empty(B, T, H, W, 64, dev, cp=64)
+            dense.conv(x, P["a12"], out=mid, n_store=64, relu=True, out2=agg, out2_coff=2 * o, n_store2=tail, relu2=True,
+                       img_bias=const_bias(P.get("a12_c"), P["a12"]))
+        else:
+            mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
+            if "a2p" in P:     # [path 2 | projection] in one launch
+                res = dense.HL.empty(B, T, H, W, cout, dev, cp=64)
+                dense.conv(x, P["a2p"], out=agg, out_coff=2 * o, n_store=tail, relu=True, out2=res, out2_coff=0,
+                           n_store2=64, relu2=False, img_bias=const_bias(P.get("a2p_c"), P["a2p"]))
+            else:
+                dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=tail, relu=True,
+                           img_bias=const_bias(P.get("a2_c"), P["a2"]))
         dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
         dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
-        # the last path also fills the padding channels of the concat tensor: its own padded output columns are exact
-        # zeros (zero weights and bias), so storing 128 - 2*o of them saves a separate fill
-        tail = min(P["a2"].bn, ap - 2 * o)
-        if 2 * o + tail < ap:                                    # fill what a2's padded columns cannot reach
-            agg.hi[..., 2 * o + tail:].zero_(); agg.lo[..., 2 * o + tail:].zero_()
-        dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=tail, relu=True,
-                   img_bias=const_bias(P.get("a2_c"), P["a2"]))
         pbias = None
         if self.use_pyramid_pooling:
             ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
@@ -193,11 +222,12 @@ class TemporalBlock(PackedModule):
             pbias = torch.empty((n_img, P["agg"].bn), dtype=torch.float32, device=dev)
             dense.pool_bias(sums, T, cin, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
                             const=const if nc else None, bias=P["agg"].bias)
-        if self.projection is not None:
-            res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"]))
-        else:
-            assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
-            res = x
+        if res is None:
+            if self.projection is not None:
+                res = dense.conv(x, P["proj"], img_bias=const_bias(P.get("proj_c"), P["proj"]))
+            else:
+                assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
+                res = x
         return dense.conv(agg, P["agg"], relu=True, img_bias=pbias, residual=res, res_after_act=True, col_sums=out_sums)
 
     def forward(self, *inputs):

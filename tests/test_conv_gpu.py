@@ -159,6 +159,31 @@ def test_column_sums_from_the_epilogue(tune):
     assert err <= 3e-5 * ref_sums.abs().max().item() + 1e-3, (err, ref_sums.abs().max().item())
 
 
+@pytest.mark.parametrize("tune", [(1, 1), (2, 1), (3, 1)])
+def test_two_destinations(tune):
+    """Two 64-column 1x1 convolutions of the same input as one 128-column launch: columns [0,64) -> a window of a concat
+    tensor with ReLU, columns [64,128) -> a second tensor without (temporal block: path 2 | projection)."""
+    B, T, C, H, W = 2, 2, 64, 21, 35
+    x = rnd(B, T, C, H, W, seed=81)
+    wA, bA = rnd(35, C, 1, 1, seed=82, scale=0.1), rnd(35, seed=83)
+    wB, bB = rnd(64, C, 1, 1, seed=84, scale=0.1), rnd(64, seed=85)
+    wm = torch.zeros(128, C, 1, 1); wm[:35] = wA; wm[64:] = wB
+    bm = torch.zeros(128); bm[:35] = bA; bm[64:] = bB
+    ib = rnd(B * T, 128, seed=86); ib[:, 35:64] = 0
+    pc = dense.pack_conv(wm.to(DEV), bm.to(DEV), bn=128)
+    cat = dense.HL.zeros(B, T, H, W, 128, DEV)
+    second = dense.HL.zeros(B, T, H, W, 64, DEV)
+    dense.conv(to_hl(x), pc, out=cat, out_coff=80, n_store=48, relu=True, out2=second, out2_coff=0, n_store2=64,
+               relu2=False, img_bias=(ib + bm).to(DEV), tune=tune)
+    torch.cuda.synchronize()
+    refA = F.relu(ref_conv2d(x, wA, bA) + ib[:, :35].view(B, T, 35, 1, 1).double())
+    refB = ref_conv2d(x, wB, bB) + ib[:, 64:].view(B, T, 64, 1, 1).double()
+    check(from_hl(cat, 80, 35), refA)
+    check(from_hl(second, 0, 64), refB)
+    assert float(cat.hi[..., :80].float().abs().max()) == 0.0                # nothing outside the window
+    assert float((cat.hi[..., 115:].float().abs() + cat.lo[..., 115:].float().abs()).max()) == 0.0   # padded columns: zeros
+
+
 def test_pair_tiling_with_fused_epilogues():
     """CTA-pair tiling with residual, per-image bias and odd image sizes (the peer CTA's rows fall off the image)."""
     B, T, C, H, W = 2, 2, 64, 9, 21
