@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace stp3 {
 
@@ -100,6 +101,8 @@ __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride
                                  const float* __restrict__ W1, const float* __restrict__ b1, int R,
                                  const float* __restrict__ W2, int CO, const float* __restrict__ bias,
                                  float* __restrict__ out, int co_stride, int accumulate) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();                      // sums / constants come from the preceding kernels
   extern __shared__ float sm[];
   float* m = sm;          // [C]
   float* v = sm + C;      // [R]
@@ -142,6 +145,8 @@ __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride
 __global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, int ci, int co,
                                     const float* __restrict__ bias, float* __restrict__ y, int co_stride,
                                     int accumulate) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   const int n = blockIdx.x;
   for (int o = threadIdx.x; o < co; o += blockDim.x) {
     float a = 0.f;
@@ -159,6 +164,8 @@ upsample2x_add_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16*
                       const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl, int ss, int s_off,
                       __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int ys, int y_off, int C8,
                       size_t total) {
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = idx % C8;
@@ -259,17 +266,17 @@ extern "C" int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int
   STP3_CHECK_ARG(sums && W1 && b1 && W2 && out && n_img > 0 && T > 0 && C > 0 && R > 0 && CO > 0 && n_const >= 0 &&
                  n_const < C && C - n_const <= sums_stride && CO <= co_stride && (n_const == 0 || const_vals),
                  "stp3_pool_bias: bad argument");
-  pool_bias_kernel<<<n_img, 256, (size_t)(C + R) * sizeof(float), (cudaStream_t)stream>>>(
-      sums, sums_stride, T, C, inv_hw, temporal, const_vals, n_const, W1, b1, R, W2, CO, bias, out, co_stride, accumulate);
-  STP3_CUDA_OK(cudaGetLastError());
+  STP3_CUDA_OK(launch_pdl(pool_bias_kernel, dim3(n_img), dim3(256), (size_t)(C + R) * sizeof(float), (cudaStream_t)stream,
+                          sums, sums_stride, T, C, inv_hw, temporal, const_vals, n_const, W1, b1, R, W2, CO, bias, out,
+                          co_stride, accumulate));
   return STP3_OK;
 }
 
 extern "C" int stp3_small_linear(const float* x, const float* W, int n, int ci, int co, const float* bias, float* y,
                                  int co_stride, int accumulate, void* stream) {
   STP3_CHECK_ARG(x && W && y && n > 0 && ci > 0 && co > 0 && co <= co_stride, "stp3_small_linear: bad argument");
-  small_linear_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(x, W, ci, co, bias, y, co_stride, accumulate);
-  STP3_CUDA_OK(cudaGetLastError());
+  STP3_CUDA_OK(launch_pdl(small_linear_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream, x, W, ci, co, bias, y,
+                          co_stride, accumulate));
   return STP3_OK;
 }
 
@@ -283,9 +290,8 @@ extern "C" int stp3_upsample2x_add(const void* x_hi, const void* x_lo, int n_img
                  y_coff % 8 == 0 && y_coff + C <= y_cstride && x_cstride % 8 == 0 && s_cstride % 8 == 0 &&
                  y_cstride % 8 == 0, "stp3_upsample2x_add: channel windows must be multiples of 8");
   const size_t total = (size_t)n_img * (2 * h) * (2 * w) * (C / 8);
-  upsample2x_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    STP3_CUDA_OK(launch_pdl(upsample2x_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
       (const bf16*)x_hi, (const bf16*)x_lo, h, w, x_cstride, (const bf16*)s_hi, (const bf16*)s_lo, s_cstride, s_coff,
-      (bf16*)y_hi, (bf16*)y_lo, y_cstride, y_coff, C / 8, total);
-  STP3_CUDA_OK(cudaGetLastError());
+      (bf16*)y_hi, (bf16*)y_lo, y_cstride, y_coff, C / 8, total));
   return STP3_OK;
 }

@@ -29,3 +29,18 @@ int set_error(int code, const char* fmt, ...);
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace stp3
+
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains; it MUST
+// execute griddepcontrol.wait (ptx::griddep_wait) before touching global memory the predecessor produced.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+

@@ -618,6 +618,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 __global__ void col_sum_reduce_kernel(const float* __restrict__ part, int n_part, int n_img, int bn,
                                       float* __restrict__ out) {
   __shared__ float sm[16][64];
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();                      // the partial rows come from the convolution just before
   const int img = blockIdx.x, c = threadIdx.x, sl = threadIdx.y;
   const int per = (n_part + 15) / 16;
   const int k0 = sl * per, k1 = min(n_part, k0 + per);
@@ -898,9 +900,8 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     STP3_CUDA_OK(cudaGetLastError());
   }
   if (p.sum_part) {
-    col_sum_reduce_kernel<<<p.n_img, dim3(64, 16), 0, stream>>>(p.sum_part, launched_grid * 4, p.n_img, 64,
-                                                      static_cast<float*>(d->col_sums));
-    STP3_CUDA_OK(cudaGetLastError());
+    STP3_CUDA_OK(launch_pdl(col_sum_reduce_kernel, dim3(p.n_img), dim3(64, 16), 0, stream, (const float*)p.sum_part,
+                            launched_grid * 4, p.n_img, 64, static_cast<float*>(d->col_sums)));
   }
   return STP3_OK;
 }
