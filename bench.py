@@ -486,9 +486,9 @@ def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
     return out
 
 
-# kernels of this repository launched by one perceive step (profiles/r01_launches_perceive_v8.csv): 43 conv_igemm,
-# lift-splat scatter + finalize + pool reduce, 3 upsample, 3 pool_bias, 3 small_linear, 2 col_sum_reduce
-LAUNCHES_PER_PERCEIVE_STEP = 57
+# kernels of this repository launched by one perceive step (profiles/r01_launches_perceive_v9.csv): 41 conv_igemm,
+# lift-splat scatter + finalize + pool reduce, 3 upsample, 3 pool_bias, 2 small_linear, 2 col_sum_reduce
+LAUNCHES_PER_PERCEIVE_STEP = 54
 
 
 if __name__ == "__main__":
