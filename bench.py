@@ -384,7 +384,7 @@ def main():
                    "achieved": alg / (ls_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
                    # dram__bytes_read+write of scatter (105.2 MB) + finalize (154.3 MB) for this workload at B=4,
-                   # profiles/r01_ncu_liftsplat_v8_summary.txt (one ncu --set full capture; scales with B)
+                   # profiles/r01_ncu_liftsplat_v10_summary.txt (one ncu --set full capture; scales with B)
                    "traffic": int(259.5e6 * b / 4) if args.workload == "perceive" else None,
                    "algorithmic_bytes_per_step": alg, "ms": ls_ms}
         line = {
@@ -409,12 +409,12 @@ def main():
             line["stage_ms"] = stage_ms
             # every extra temporal block (stress: 4 instead of 2) adds 5 convs + 3 small kernels
             line["gpu_launches"] = 2 * K * (LAUNCHES_PER_PERCEIVE_STEP + 8 * max(0, cfg.receptive_field - 3))
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN> family (temporal model + decoder, 45 launches/step)",
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> family (temporal model + decoder, 41 launches/step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
-                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v8_summary.txt
-                                # (temporal model + first decoder convs, B=4): 4248 MB read + 2223 MB written
-                                "traffic": int(6471e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 45 launches (ncu --set full, cold cache)",
+                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v10_summary.txt
+                                # (the temporal model's 16 + the first 6 decoder convs, B=4): 4093 MB read + 2330 MB written
+                                "traffic": int(6423e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 41 launches (ncu --set full, cold cache)",
                                 "algorithmic_flops_per_step": flops, "ms": dense_ms,
                                 "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
             line["roofline_lift_splat"] = roof_ls

@@ -1,6 +1,6 @@
 """Text summaries of the round's `ncu --set full` captures (tools/profile_round.sh) for profiles/.
 
-  python tools/ncu_summaries.py gpurun_out/r01_v8 profiles/r01
+  python tools/ncu_summaries.py gpurun_out/r01_v10 profiles/r01 v10
 """
 import csv
 import subprocess
@@ -66,6 +66,6 @@ def liftsplat(rep, dst):
 
 
 if __name__ == "__main__":
-    src, dst = sys.argv[1], sys.argv[2]
-    conv(src + "_conv_full.ncu-rep", dst + "_ncu_conv_v8_summary.txt")
-    liftsplat(src + "_liftsplat_full.ncu-rep", dst + "_ncu_liftsplat_v8_summary.txt")
+    src, dst, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+    conv(src + "_conv_full.ncu-rep", f"{dst}_ncu_conv_{tag}_summary.txt")
+    liftsplat(src + "_liftsplat_full.ncu-rep", f"{dst}_ncu_liftsplat_{tag}_summary.txt")
