@@ -713,7 +713,9 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const int want_group = want_group_raw & 3;
   static const bool use_pdl = [] { const char* e = getenv("STP3_CONV_PDL"); return !e || atoi(e) != 0; }();
   const bool stream_weights = (want_group_raw & 4) != 0;    // +4: keep the weights in the ring even if they would fit
-  const bool stack = (want_group_raw & 8) != 0 && d->bn == 64;   // +8: stacked [W_hi; W_lo] operand (bn = 64 only)
+  // +8: stacked [W_hi; W_lo] operand (bn = 64 only).  Untuned (tune_group == 0) multi-tap 64-column layers use it: it
+  // won on every such layer of the hot path (profiles/r01_autotune_v9.txt)
+  const bool stack = d->bn == 64 && ((want_group_raw & 8) != 0 || (want_group_raw == 0 && d->ntaps > 1));
   // taps that can share one activation load: runs (<= 4) of consecutive taps with the same (dt, dx) and dy advancing
   // by the stride
   ConvParams p;
@@ -733,7 +735,8 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const int n_img_ = d->B * d->T;
   const long long tiles16 = (long long)n_img_ * ceil_div(d->Wo, kTileW) * ceil_div(d->Ho, 2 * kSubH);
   // tune_n_sub == 3: the 16x16 tile is shared by a CTA pair (cta_group::2), 8 image rows per CTA
-  const bool pair = want_nsub == 3;
+  // untuned (tune_n_sub == 0) multi-tap layers take the pair tiling, the autotuner's choice on all of them
+  const bool pair = want_nsub == 3 || (want_nsub == 0 && d->ntaps > 1);
   const int n_sub = pair ? 1 : (want_nsub == 1 || want_nsub == 2 ? want_nsub : (tiles16 >= 3 * 148 ? 2 : 1));
   const int tile_h = pair ? 2 * kSubH : kSubH * n_sub;
   const int box_h = kSubH * n_sub + (group - 1);                         // image rows one CTA loads per stage
