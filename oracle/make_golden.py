@@ -1,6 +1,6 @@
 """Generates tests/golden/lift_splat_*.npz by running the UNMODIFIED reference (imported from
 /root/reference through oracle/ref_loader.py) on seeded synthetic inputs, on the CPU of the build
-container.  Test infrastructure; run by hand:  python -m oracle.make_golden
+container.  Test infrastructure; run by hand:  python -m oracle.make_golden [case ...]
 
 The reference has no tests/fixtures of its own, so these files are what pins the
 oracle (oracle/lift_splat_oracle.py) and, through it, the CUDA path.  What is stored:
@@ -30,6 +30,8 @@ CASES = [  # name, config, batch, seed, random_pose, store_full
     ("carla_res", "carla_res", 1, 3, True, False),
     ("lift_splat", "lift_splat", 1, 0, False, False),
     ("perceive", "perceive", 1, 0, False, False),
+    # BASELINE configs[4]: 400x400 BEV, D=96, C=128, S=5 (4.8 M frustum points), non-level cameras
+    ("stress", "stress", 1, 5, True, False),
 ]
 
 
@@ -65,7 +67,10 @@ def run_reference(ref, cfg, inp):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    only = set(sys.argv[1:])                      # optional: regenerate just the named cases
     for name, cfg_name, batch, seed, rp, full in CASES:
+        if only and name not in only:
+            continue
         cfg = syn.CONFIGS[cfg_name]
         inp = syn.lift_inputs(cfg, batch, seed=seed, random_pose=rp)
         fake, geom, rank, bev = run_reference(ref, cfg, inp)

@@ -7,7 +7,7 @@ import numpy as np
 from stp3_b200.utils import synthetic as syn
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-LIFT_CASES = ["tiny_randpose", "tiny_level", "plumbing", "carla_res", "lift_splat", "perceive"]
+LIFT_CASES = ["tiny_randpose", "tiny_level", "plumbing", "carla_res", "lift_splat", "perceive", "stress"]
 
 
 def sha(a) -> str:
