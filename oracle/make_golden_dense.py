@@ -34,6 +34,16 @@ def main():
         y = tm(x)
         np.savez_compressed(os.path.join(OUT, "dense_temporal_model.npz"), out=y.numpy(), H=H, W=W, seed=1, in_seed=5)
         print("temporal_model", tuple(y.shape), float(y.abs().max()))
+        # stress shape (BASELINE configs[4]): 128 + 6 input channels, receptive field 5 -> four blocks, the first with
+        # 67-channel paths
+        Hs, Ws = 16, 24
+        tms = TD.init_exact(ref.temporal_model.TemporalModel(134, 5, (Hs, Ws), start_out_channels=64), seed=3).eval()
+        xs = dense_input((1, 5, 134, Hs, Ws), 7)
+        xs[:, :, 128:] = xs[:, :, 128:, :1, :1]
+        ys = tms(xs)
+        np.savez_compressed(os.path.join(OUT, "dense_temporal_model_stress.npz"), out=ys.numpy(), H=Hs, W=Ws, seed=3,
+                            in_seed=7)
+        print("temporal_model (stress shape)", tuple(ys.shape), float(ys.abs().max()))
         for name, gates in (("perceive", GATES_PERCEIVE), ("all", GATES_ALL)):
             dec = TD.init_exact(ref.decoder.Decoder(64, 2, 3, 2, gates), seed=2).eval()
             x = dense_input((1, 3, 64, H, W), 6)

@@ -101,6 +101,18 @@ def test_temporal_model_vs_reference_golden_and_fp64():
     close(y, torch.from_numpy(g["out"]))                  # the reference's own fp32 output
 
 
+def test_temporal_model_stress_shape_vs_reference_golden():
+    """BASELINE configs[4] shape (134 input channels, receptive field 5) against the reference's own fp32 output."""
+    g = dict(np.load(os.path.join(GOLDEN, "dense_temporal_model_stress.npz")))
+    H, W = int(g["H"]), int(g["W"])
+    x = dense_input((1, 5, 134, H, W), int(g["in_seed"]))
+    x[:, :, 128:] = x[:, :, 128:, :1, :1]
+    with torch.no_grad():
+        tm = TD.init_exact(TemporalModel(134, 5, (H, W), start_out_channels=64), seed=int(g["seed"])).eval()
+        y = tm.to(DEV)(x.to(DEV))
+    close(y, torch.from_numpy(g["out"]))
+
+
 def test_temporal_model_constant_channels_as_bias():
     """The fused path never materialises the 6 broadcast ego-motion channels (stp3.py:145-152)."""
     g, x = _temporal_golden()

@@ -33,6 +33,19 @@ def test_temporal_model_restatement_matches_reference_output():
     assert (y - ref).abs().max() <= 2e-5 * ref.abs().max()
 
 
+def test_temporal_model_restatement_matches_reference_output_stress_shape():
+    """BASELINE configs[4] shape: 134 input channels (128 + ego-motion), receptive field 5 (four blocks)."""
+    g = load("dense_temporal_model_stress.npz")
+    H, W = int(g["H"]), int(g["W"])
+    with torch.no_grad():
+        tm = TD.init_exact(TemporalModel(134, 5, (H, W), start_out_channels=64), seed=int(g["seed"])).eval()
+        x = dense_input((1, 5, 134, H, W), int(g["in_seed"]))
+        x[:, :, 128:] = x[:, :, 128:, :1, :1]
+        y = TD.temporal_model(x, tm)
+    ref = torch.from_numpy(g["out"])
+    assert y.shape == ref.shape and (y - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
 @pytest.mark.parametrize("name,gates", [("perceive", GATES_PERCEIVE), ("all", GATES_ALL)])
 def test_decoder_restatement_matches_reference_output(name, gates):
     g = load(f"dense_decoder_{name}.npz")
