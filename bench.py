@@ -113,8 +113,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_problem(cfg, batch, seed):
-    inp = syn.lift_inputs(cfg, batch, seed=seed)
+def make_problem(cfg, batch, seed, tilt_deg=0.0):
+    """Batch of `batch` samples with per-sample seeds seed, seed+1, ...: sample i == lift_inputs(cfg, 1, seed+i), so
+    the sample with seed 0 is the one the end-to-end reference fixture (tests/golden/e2e_perceive_*.npz) was recorded on."""
+    inp = syn.stack_samples(cfg, [seed + i for i in range(batch)], tilt_deg=tilt_deg)
     cam_M, cam_t, ego_R, ego_t = G.lift_matrices(inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
     xs, ys, ds = G.frustum_axes(cfg.final_dim, cfg.downsample, cfg.d_bound)
     res, start, dim = G.calculate_birds_eye_view_parameters(cfg.x_bound, cfg.y_bound, cfg.z_bound)
@@ -143,80 +145,194 @@ def build_model(device=None, lcfg=None):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_step(workload, cfg, prob, model):
-    """One sample through the CPU port of the reference's path (oracle/torch_port.py + oracle/torch_dense.py: the same
-    ATen operator sequence as the reference, which cannot travel to the GPU box)."""
-    from oracle import torch_port as TP
-    inp = prob["inp"]
-    xs, ys, ds = prob["axes"]
-    with torch.no_grad():
-        bev = TP.lift_splat(inp["feat"][:1], inp["depth_logits"][:1], inp["intrinsics"][:1], inp["extrinsics"][:1],
-                            inp["future_egomotion"][:1], xs, ys, ds, prob["res"], prob["start"], prob["dim"],
-                            cfg.discount)
-        if workload == "lift_splat":
-            return bev
-        from oracle import torch_dense as TD
-        ego = inp["future_egomotion"][:1]
-        ego = torch.cat([torch.zeros_like(ego[:, :1]), ego[:, :-1]], 1)
-        x = torch.cat([bev, ego.view(1, -1, 6, 1, 1).expand(1, ego.shape[1], 6, *bev.shape[-2:])], dim=2)
-        return TD.decoder(TD.temporal_model(x, model.temporal_model), model.decoder)
+def workload_config(args, cfg, world):
+    """`config` of the JSON line: identical for the B200 arm and the reference arm (it names the workload)."""
+    X, Y = cfg.bev_xy
+    return {"workload": WORKLOADS[args.workload], "samples_per_gpu_per_step": args.batch,
+            "global_batch": args.batch * world, "cameras": cfg.n_cameras, "frames": cfg.receptive_field, "bev": [X, Y],
+            "channels": cfg.out_channels, "depth_bins": cfg.n_depth,
+            "parallelism": f"dp{world} (batch sharded, no collective on the forward path)",
+            "l2": "flushed between timed iterations (256 MiB write)", "weights": "random init, seeded",
+            "rig": "level cameras (SURVEY.md 8d); roofline_lift_splat also times the 1-degree tilted rig"}
 
 
-def pick_threads(cfg, prob):
-    """The eager CPU path is dominated by small ops and slows down when oversubscribed: give it its best thread count."""
-    from oracle import torch_port as TP
-    inp = prob["inp"]
-    xs, ys, ds = prob["axes"]
-    cores = os.cpu_count() or 1
-    best, best_t = cores, float("inf")
-    for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
-        torch.set_num_threads(n)
-        t0 = time.perf_counter()
-        with torch.no_grad():   # one frame of one sample
-            TP.lift_splat(inp["feat"][:1, :1], inp["depth_logits"][:1, :1], inp["intrinsics"][:1, :1],
-                          inp["extrinsics"][:1, :1], inp["future_egomotion"][:1, :1], xs, ys, ds, prob["res"],
-                          prob["start"], prob["dim"], cfg.discount)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-    torch.set_num_threads(best)
-    return best
+class ReferenceArm:
+    """The reference's own CPU implementation of the path on the host cores.  kind "reference": the UNMODIFIED
+    reference package (installed by oracle/build_ref.py into the git-ignored baseline/_ref/, or /root/reference in the
+    build container) -- its STP3.get_geometry / projection_to_birds_eye_view, TemporalModel and Decoder -- imported
+    through oracle/ref_loader.py; kind "port": the op-for-op CPU port under oracle/ when that install is absent."""
 
+    def __init__(self, workload, cfg):
+        from oracle import ref_loader
+        self.workload, self.cfg = workload, cfg
+        self.prob = make_problem(cfg, 1, seed=0)
+        self.model = build_model(lcfg=cfg) if workload in PERCEPTION else None
+        self.kind = "port"
+        if ref_loader.reference_available():
+            try:
+                self._init_reference(ref_loader)
+                self.kind = "reference"
+            except Exception as e:              # e.g. a stub missing on this box: fall back to the port, say so
+                print(f"reference import failed ({type(e).__name__}: {e}); timing the CPU port instead", file=sys.stderr)
 
-def time_reference(workload, cfg, steps, warmup):
-    prob = make_problem(cfg, 1, seed=0)
-    model = build_model(lcfg=cfg) if workload in PERCEPTION else None
-    threads = pick_threads(cfg, prob)
-    for _ in range(warmup):
-        reference_step(workload, cfg, prob, model)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        reference_step(workload, cfg, prob, model)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return 1.0 / dt, dt, threads
+    def _init_reference(self, ref_loader):
+        from oracle.make_golden_dense import GATES_PERCEIVE
+        self.ref = ref_loader.load_reference()
+        cfg = self.cfg
+        if self.model is not None:
+            X, Y = cfg.bev_xy
+            with torch.no_grad():
+                self.ref_tm = self.ref.temporal_model.TemporalModel(cfg.out_channels + 6, cfg.receptive_field, (X, Y),
+                                                                    start_out_channels=64).eval()
+                self.ref_tm.load_state_dict(self.model.temporal_model.state_dict(), strict=True)
+                self.ref_dec = self.ref.decoder.Decoder(64, 2, cfg.receptive_field, 2, GATES_PERCEIVE).eval()
+                self.ref_dec.load_state_dict(self.model.decoder.state_dict(), strict=True)
+
+    def step(self):
+        """One sample through the path."""
+        inp, cfg = self.prob["inp"], self.cfg
+        with torch.no_grad():
+            if self.kind == "reference":
+                from oracle.make_golden import run_reference
+                bev = run_reference(self.ref, cfg, inp)[3]
+            else:
+                from oracle import torch_port as TP
+                xs, ys, ds = self.prob["axes"]
+                bev = TP.lift_splat(inp["feat"], inp["depth_logits"], inp["intrinsics"], inp["extrinsics"],
+                                    inp["future_egomotion"], xs, ys, ds, self.prob["res"], self.prob["start"],
+                                    self.prob["dim"], cfg.discount)
+            if self.workload == "lift_splat":
+                return bev
+            ego = inp["future_egomotion"]
+            ego = torch.cat([torch.zeros_like(ego[:, :1]), ego[:, :-1]], 1)
+            x = torch.cat([bev, ego.view(1, -1, 6, 1, 1).expand(1, ego.shape[1], 6, *bev.shape[-2:])], dim=2)
+            if self.kind == "reference":
+                return self.ref_dec(self.ref_tm(x))
+            from oracle import torch_dense as TD
+            return TD.decoder(TD.temporal_model(x, self.model.temporal_model), self.model.decoder)
+
+    def pick_threads(self):
+        """Thread count by timing the WHOLE step (after one warm-up step at the first candidate): the eager CPU path
+        mixes tiny ops (which slow down when oversubscribed) with 194 GFLOP of convolutions (which want the cores)."""
+        cores = os.cpu_count() or 1
+        cands = sorted({min(cores, c) for c in (8, 16, 32, 64, cores)})
+        torch.set_num_threads(cands[0])
+        self.step()
+        best, best_t, sweep = cands[0], float("inf"), {}
+        for n in cands:
+            torch.set_num_threads(n)
+            t0 = time.perf_counter()
+            self.step()
+            sweep[n] = time.perf_counter() - t0
+            if sweep[n] < best_t:
+                best, best_t = n, sweep[n]
+        torch.set_num_threads(best)
+        return best, sweep
+
+    def time(self, steps, warmup):
+        threads, sweep = self.pick_threads()
+        for _ in range(warmup):
+            self.step()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.step()
+            times.append(time.perf_counter() - t0)
+        dt = statistics.median(times)
+        return {"fps": 1.0 / dt, "dt": dt, "threads": threads, "times": times,
+                "sweep": {str(k): round(v, 3) for k, v in sweep.items()}}
+
+    def describe(self, r, steps, warmup):
+        what = ("unmodified reference package (baseline/_ref or /root/reference via oracle/ref_loader.py): STP3.get_geometry + "
+                "projection_to_birds_eye_view" + (" + TemporalModel + Decoder" if self.workload in PERCEPTION else "")
+                if self.kind == "reference" else
+                "op-for-op CPU port of the reference (oracle/torch_port.py" + (" + oracle/torch_dense.py)" if self.workload in PERCEPTION else ")"))
+        return (f"1 sample (6 cam x {self.cfg.receptive_field} t) of the step's batch per timed step through the {what}; median of "
+                f"{steps} step(s) after {warmup} warm-up; {r['threads']} of {os.cpu_count()} host threads = best of a whole-step "
+                f"sweep {r['sweep']} s")
 
 
 def run_reference_arm(args, cfg):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    fps, dt, threads = time_reference(args.workload, cfg, steps, warmup)
-    sample = (f"1 sample (6 cam x {cfg.receptive_field} t) per step, {steps} timed step(s) after {warmup} warm-up, "
-              f"{threads} of {os.cpu_count()} host threads (best of a short sweep)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, min(args.steps, 40)), min(args.warmup, 5)      # bounded: one sample takes seconds
+    arm = ReferenceArm(args.workload, cfg)
+    r = arm.time(steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "batch_per_step": 1,
-                   "path": "oracle/torch_port.py + oracle/torch_dense.py: op-for-op CPU port of the reference "
-                           "(/root/reference is pure Python and cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": r["dt"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, world),
+        "cpu_baseline": {"value": r["fps"], "unit": UNIT, "cores": r["threads"], "kind": arm.kind,
+                         "sample": arm.describe(r, steps, warmup)},
+        "e2e": {"value": r["fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+OUR_KERNELS = ("conv_igemm", "lift_splat", "bev_finalize", "bev_discount", "pool_reduce", "pool_bias", "small_linear",
+               "upsample2x", "col_sum_reduce", "hilo", "spatial_sum", "clear_bytes", "lift_splat_bwd")
+
+
+def count_launches(step_fn, dev):
+    """Kernel launches of ONE step, observed with CUPTI (torch.profiler) in this run: (this repository's kernels,
+    all kernels, device time of the conv_igemm family in ms).  Not inside the timed region."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize(dev)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn()
+            torch.cuda.synchronize(dev)
+        ours = total = 0
+        conv_us = 0.0
+        for ev in prof.events():
+            if "memcpy" in ev.name.lower() or "memset" in ev.name.lower():
+                continue
+            total += 1
+            if any(k in ev.name for k in OUR_KERNELS):
+                ours += 1
+            if "conv_igemm" in ev.name:
+                conv_us += float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
+        return ours, total, conv_us * 1e-3
+    except Exception as e:                                  # CUPTI unavailable: say so instead of guessing
+        print(f"launch count unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+        return None, None, None
+
+
+def fast_path_fraction(ranks):
+    """Share of (image, depth bin, image column) segments whose in-grid points all fall into ONE pillar -- the case the
+    scatter kernel handles with 8 FFMA per LDS.128; the others take the segmented walk.  ranks (B,S,N,D,Hf,Wf) int32."""
+    r = ranks.long()
+    valid = r >= 0
+    big = torch.where(valid, r, torch.full_like(r, 1 << 40)).amin(dim=-2)
+    small = torch.where(valid, r, torch.full_like(r, -1)).amax(dim=-2)
+    some = valid.any(dim=-2)
+    uni = (big == small) & some
+    return float(uni.sum().item()) / max(1.0, float(some.sum().item()))
+
+
+def check_parity(res, cfg):
+    """One replayed step's outputs for sample 0 (seed 0) against the end-to-end reference fixture (the unmodified
+    reference and the fp64 oracle at the headline size).  Raises if the north-star bar (1e-3 of max) is missed."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "e2e_perceive_level.npz")
+    g = np.load(path)
+    worst_o = worst_r = 0.0
+    for k in ("segmentation", "pedestrian", "hdmap"):
+        flat = res[k][0].detach().double().cpu().numpy().reshape(-1)
+        got = flat[g[f"{k}_index"]]
+        m = float(g[f"{k}_max"])
+        worst_o = max(worst_o, float(np.abs(got - g[f"{k}_oracle"]).max()) / m)
+        worst_r = max(worst_r, float(np.abs(got - g[f"{k}_ref"].astype(np.float64)).max()) / m)
+    if not (worst_r <= 1e-3 and worst_o <= 1e-3):
+        raise SystemExit(f"bench.py: the timed step's logits miss the parity bar: {worst_o:.2e} of max vs the fp64 oracle, "
+                         f"{worst_r:.2e} vs the reference (bar 1e-3) -- refusing to report a throughput for wrong results")
+    return {"fixture": "tests/golden/e2e_perceive_level.npz (reference end to end at 200x200, sample seed 0)",
+            "max_err_vs_fp64_oracle": worst_o, "max_err_vs_reference_fp32": worst_r, "bar": 1e-3,
+            "checked": "segmentation, pedestrian, hdmap logits of sample 0 of a replayed (graphed) step, 40k entries each"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,9 +341,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="perceive", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU per step (perceive config 4: 32 / 8 GPUs)")
+    ap.add_argument("--rig", default="level", choices=["level", "tilted"],
+                    help="camera rig of the timed workload (the lift-splat roofline always reports both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: serialise H2D, compute and D2H of every step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained run, the second rig and the latency mode")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the resident timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -254,8 +373,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, K, b = max(args.warmup, 3), args.steps, args.batch
     perceive = args.workload in PERCEPTION
+    tilt = 1.0 if args.rig == "tilted" else 0.0
 
-    prob = make_problem(cfg, b, seed=rank)          # every rank works on its own shard of the global batch
+    prob = make_problem(cfg, b, seed=rank * b, tilt_deg=tilt)   # every rank works on its own shard of the global batch
     inp = prob["inp"]
     host = {k: inp[k].pin_memory() for k in ("feat", "depth_logits", "intrinsics", "extrinsics", "future_egomotion")}
     host_mats = [m.pin_memory() for m in prob["mats"]]
@@ -343,6 +463,12 @@ def main():
 
     for _ in range(W):
         step_resident()
+    # parity gate: the step that is about to be timed must produce the reference's logits
+    parity = None
+    if rank == 0 and args.workload == "perceive" and args.rig == "level":
+        res0 = step_resident()
+        torch.cuda.synchronize()
+        parity = check_parity(res0, cfg)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -365,10 +491,45 @@ def main():
         e2e_ms = timed(step_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
 
+    # sustained figure: the same resident step back to back for >= 2 s (the 20-step region above is a ~65 ms burst)
+    sustained = None
+    if not args.no_extras:
+        n_sus = max(K, int(2000.0 / max(total_ms / K, 1e-3)) + 1)
+        sus_ms = timed(step_resident, n_sus)
+        sustained = {"value": b * world / (sus_ms / n_sus * 1e-3), "unit": UNIT, "steps": n_sus,
+                     "ms_per_step": sus_ms / n_sus, "seconds": sus_ms * 1e-3}
+
     # per-stage device time: each stage captured as its own CUDA graph (no launch gaps), timed with CUDA events
     stage_ms = {}
     if perceive:
         stage_ms = time_stages(model, graphed.static if graphed is not None else None, d_feat, d_depth, inp, flush, dev)
+    ours, total_launches, conv_ms_prof = count_launches(step_resident, dev)
+
+    # the lift-splat on both rigs (level cameras = SURVEY 8d; 1 degree of roll / pitch / yaw error per camera)
+    rigs = {}
+    if not args.no_extras and args.workload != "stress":
+        for name, tdeg in (("level", 0.0), ("tilted_1deg", 1.0)):
+            pr = make_problem(cfg, b, seed=rank * b, tilt_deg=tdeg)
+            f, d = pr["inp"]["feat"].to(dev), pr["inp"]["depth_logits"].to(dev)
+            mats = [m.to(dev) for m in pr["mats"]]
+            o = torch.empty((b, cfg.receptive_field, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
+            ws = ops.Workspace()
+
+            def ls():
+                ops.lift_splat(f, d, *mats, xs, ys, ds, pr["off"], pr["res"], pr["dim"], cfg.discount, out=o, workspace=ws)
+            _, ranks = ops.lift_splat(f[:1], d[:1], *[m[:1] for m in mats], xs, ys, ds, pr["off"], pr["res"], pr["dim"],
+                                      cfg.discount, return_ranks=True)
+            fpf = fast_path_fraction(ranks)
+            for _ in range(3):
+                ls()
+            ms = timed(ls, 10) / 10
+            rigs[name] = {"ms": ms, "fast_path_fraction": fpf}
+            del f, d, o
+
+    # latency mode (north_star): global batch 1 < #GPUs, camera frames sharded, ONE all-gather of raw BEV frames
+    latency = None
+    if world > 1 and perceive and not args.no_extras:
+        latency = time_latency_mode(model, cfg, dev, flush, rank, world)
 
     if rank == 0:
         ms_per_step = total_ms / K
@@ -383,57 +544,113 @@ def main():
         roof_ls = {"bound": "hbm", "kernel": "lift-splat (scatter + finalize, one C-ABI call)",
                    "achieved": alg / (ls_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": alg / (ls_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
-                   # dram__bytes_read+write of scatter (105.2 MB) + finalize (154.3 MB) for this workload at B=4,
-                   # profiles/r01_ncu_liftsplat_v10_summary.txt (one ncu --set full capture; scales with B)
-                   "traffic": int(259.5e6 * b / 4) if args.workload == "perceive" else None,
-                   "algorithmic_bytes_per_step": alg, "ms": ls_ms}
+                   "traffic": TRAFFIC["lift_splat"]["bytes_per_sample"] * b if args.workload == "perceive" else None,
+                   "traffic_source": TRAFFIC["lift_splat"]["source"],
+                   "algorithmic_bytes_per_step": alg, "ms": ls_ms, "rig": args.rig}
+        for name, r in rigs.items():
+            r["achieved"] = alg / (r["ms"] * 1e-3) / 1e9
+            r["frac"] = r["achieved"] / pk["hbm_gbs"]
+        if rigs:
+            roof_ls["rigs"] = rigs
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (dense layers: bf16x3 split products, fp32 accumulate)" if perceive else "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "samples_per_gpu_per_step": b, "global_batch": frames,
-                       "cameras": cfg.n_cameras, "frames": cfg.receptive_field, "bev": [X, Y],
-                       "channels": cfg.out_channels, "depth_bins": cfg.n_depth,
-                       "parallelism": f"dp{world} (batch sharded, no collective on the forward path)",
-                       "l2": "flushed between timed iterations (256 MiB write)", "weights": "random init, seeded"},
+            "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mode": e2e_mode},
+            "parity_checked": parity is not None, "parity": parity,
+            "sustained": sustained,
         }
+        if args.rig != "level":
+            line["config"]["rig"] = "tilted: every camera 1 degree off level (timed workload)"
+        # launches inside the resident + e2e timed regions (2K steps), counted by CUPTI on one step of this run
+        line["gpu_launches"] = 2 * K * ours if ours is not None else None
+        line["launches_per_step"] = {"ours": ours, "all_kernels": total_launches, "how": "torch.profiler (CUPTI), one replayed step of this run"}
         if perceive:
             dense_ms = stage_ms.get("temporal_model", 0.0) + stage_ms.get("decoder", 0.0)
             # the flop count was taken on the reference modules for the perceive configuration only
             flops = (GFLOP_TEMPORAL + GFLOP_DECODER) * 1e9 * b if args.workload == "perceive" else None
             ach = flops / (dense_ms * 1e-3) / 1e12 if flops and dense_ms > 0 else None
             line["stage_ms"] = stage_ms
-            # every extra temporal block (stress: 4 instead of 2) adds 5 convs + 3 small kernels
-            line["gpu_launches"] = 2 * K * (LAUNCHES_PER_PERCEIVE_STEP + 8 * max(0, cfg.receptive_field - 3))
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> family (temporal model + decoder, 41 launches/step)",
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> family (temporal model + decoder)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
-                                # dram bytes of the 22 conv launches captured in profiles/r01_ncu_conv_v10_summary.txt
-                                # (the temporal model's 16 + the first 6 decoder convs, B=4): 4093 MB read + 2330 MB written
-                                "traffic": int(6423e6 * b / 4) if args.workload == "perceive" else None, "traffic_note": "22 of 41 launches (ncu --set full, cold cache)",
+                                "traffic": TRAFFIC["conv"]["bytes_per_sample"] * b if args.workload == "perceive" else None,
+                                "traffic_source": TRAFFIC["conv"]["source"],
                                 "algorithmic_flops_per_step": flops, "ms": dense_ms,
-                                "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity"}
+                                "conv_kernel_ms_cupti": conv_ms_prof,
+                                "note": "algorithmic 2*MAC flops of the fp32 layers; the kernel issues 3 bf16 MMAs per product (hi*hi+hi*lo+lo*hi) to hold 1e-3 parity: "
+                                        "profiles/r02_precision_plan.txt shows every 2-MMA form missing the bar"}
             line["roofline_lift_splat"] = roof_ls
         else:
-            line["gpu_launches"] = 2 * K * 2
             line["roofline"] = roof_ls
+        if latency is not None:
+            line["latency_mode"] = latency
         if perceive and os.environ.get("STP3_TUNE_REPORT"):
             from stp3_b200 import dense
             for desc, times in dense.TUNE_LOG:
                 print("TUNE", desc.ljust(44), "  ".join(f"{k}:{v * 1e3:7.1f}us" for k, v in times.items()), file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
-            fps, dt, threads = time_reference(args.workload, cfg, 1, 0)       # picks its own (best) thread count
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"1 sample through the op-for-op CPU port of the reference (oracle/torch_port.py"
-                                              f"{' + oracle/torch_dense.py' if perceive else ''}), 1 run, {threads} threads"}
+            arm = ReferenceArm(args.workload, cfg)
+            r = arm.time(3, 1)
+            line["cpu_baseline"] = {"value": r["fps"], "unit": UNIT, "cores": r["threads"], "kind": arm.kind,
+                                    "sample": arm.describe(r, 3, 1)}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) cannot be measured outside ncu: static values from the
+# committed `ncu --set full` captures, per sample
+TRAFFIC = {
+    "lift_splat": {"bytes_per_sample": int(259.5e6 / 4), "source": "static: profiles/r01_ncu_liftsplat_v10_summary.txt (scatter + finalize, B=4)"},
+    "conv": {"bytes_per_sample": int(6423e6 / 4), "source": "static: profiles/r01_ncu_conv_v10_summary.txt (22 of 41 conv launches, cold cache, B=4)"},
+}
+
+
+def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
+    """Global batch 1 on `world` GPUs: STP3.forward_features_frame_sharded (each rank splats its share of the B*S camera
+    frames, ONE NCCL all-gather of raw BEV frames, replicated temporal model + decoder) next to the unsharded forward
+    of the same sample on every rank.  Eager launches on both sides (NCCL is not captured in a graph here); device
+    times by CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from stp3_b200 import parallel
+    inp = syn.lift_inputs(cfg, 1, seed=0)
+    a = (inp["feat"].to(dev), inp["depth_logits"].to(dev), inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+    X, Y = cfg.bev_xy
+    S, C = cfg.receptive_field, cfg.out_channels
+    with torch.no_grad():
+        for _ in range(3):
+            sh = model.forward_features_frame_sharded(*a)
+            full = model.forward_features(*a)
+        torch.cuda.synchronize()
+        err = max(float((sh[k] - full[k]).abs().max() / full[k].abs().max()) for k in ("segmentation", "pedestrian", "hdmap"))
+
+        def timed(fn):
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                dist.barrier()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); fn(); e.record()
+                torch.cuda.synchronize()
+                tot += s.elapsed_time(e)
+            return parallel.max_over_ranks(tot / reps, dev)
+        ms_sharded = timed(lambda: model.forward_features_frame_sharded(*a))
+        ms_full = timed(lambda: model.forward_features(*a))
+        f0, fc = parallel.shard_batch(S, rank, world)
+        raw = torch.zeros((fc, X, Y, C), dtype=torch.float32, device=dev)
+        ms_ag = timed(lambda: parallel.all_gather_frames(raw, S))
+        cmax = max(parallel.shard_batch(S, r, world)[1] for r in range(world))
+    err = parallel.max_over_ranks(err, dev)
+    return {"global_batch": 1, "frames_per_rank": [parallel.shard_batch(S, r, world)[1] for r in range(world)],
+            "ms": ms_sharded, "ms_unsharded_same_sample": ms_full, "allgather_ms": ms_ag,
+            "bytes": int(world * cmax * X * Y * C * 4), "bytes_note": "all_gather_into_tensor output per rank (padded to equal shards)",
+            "parity_vs_unsharded": err <= 1e-4, "max_rel_err_vs_unsharded": err, "launch": "eager (Python/ctypes launches on both sides)"}
 
 
 def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
@@ -484,11 +701,6 @@ def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
                 tot += a.elapsed_time(c)
             out[name] = tot / reps
     return out
-
-
-# kernels of this repository launched by one perceive step (profiles/r01_launches_perceive_v9.csv): 41 conv_igemm,
-# lift-splat scatter + finalize + pool reduce, 3 upsample, 3 pool_bias, 2 small_linear, 2 col_sum_reduce
-LAUNCHES_PER_PERCEIVE_STEP = 54
 
 
 if __name__ == "__main__":

@@ -13,7 +13,11 @@ import sys
 import types
 from types import SimpleNamespace
 
-REFERENCE_ROOT = os.environ.get("STP3_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the reference where it lies (build container), else its unmodified install under the git-ignored baseline/_ref/
+# (oracle/build_ref.py; that copy travels to the GPU box)
+_CANDIDATES = [os.environ.get("STP3_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "stp3"))), "/root/reference")
 
 
 def reference_available() -> bool:

@@ -253,6 +253,8 @@ class GraphedPerception:
         }
         self.pinned = {k: torch.zeros(v.shape, dtype=torch.float32).pin_memory()
                        for k, v in self.static.items() if k not in ("feat", "depth_logits")}
+        self.h2d_done = torch.cuda.Event()      # the pinned staging buffers may be rewritten once this has fired
+        self.h2d_done.record(torch.cuda.current_stream(dev))
         with torch.no_grad():
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -261,18 +263,41 @@ class GraphedPerception:
                     model.forward_device(**self.static)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            # the graph bakes in the device pointers of the packed / folded weights: remember which parameter versions
+            # they were derived from, and keep the packed tensors alive for as long as the graph exists
+            self._packed_modules = [m for m in model.modules() if hasattr(m, "packed") and "_packed_cache" in m.__dict__]
+            self._signatures = [m._signature() for m in self._packed_modules]
+            self._keepalive = [m.__dict__["_packed_cache"] for m in self._packed_modules]
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = model.forward_device(**self.static)
 
-    def __call__(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+    def check_weights_unchanged(self):
+        """Raises if a parameter or buffer the captured kernels read was modified (load_state_dict, optimizer step,
+        .to()) after the capture: the graph would keep replaying the old packed weights."""
+        for m, sig in zip(self._packed_modules, self._signatures):
+            if m._signature() != sig:
+                raise RuntimeError(f"{type(m).__name__}: parameters changed after the CUDA graph was captured; build a new "
+                                   "GraphedPerception (the graph holds the packed weights of the old values)")
+
+    def stage_inputs(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion, stream=None):
+        """Host-side calibration math + the (asynchronous) copies into the graph's static input buffers.  The pinned
+        staging buffers are reused every call: wait until the previous call's H2D copies have left them."""
+        self.check_weights_unchanged()
         host = self.model.prepare_inputs(intrinsics, extrinsics, future_egomotion)
+        self.h2d_done.synchronize()
         for k, v in host.items():
             self.pinned[k].copy_(v)
             self.static[k].copy_(self.pinned[k], non_blocking=True)
+        self.h2d_done.record(stream if stream is not None else torch.cuda.current_stream(self.static["feat"].device))
         S = self.model.receptive_field
         self.static["feat"].copy_(feat[:, :S], non_blocking=True)
         self.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
+
+    def __call__(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+        """Inputs are consumed asynchronously (pinned host tensors must stay untouched until the step has run); the
+        returned tensors are the graph's static output buffers, valid until the next call."""
+        self.stage_inputs(feat, depth_logits, intrinsics, extrinsics, future_egomotion)
         self.graph.replay()
         return self.out
 
@@ -307,16 +332,10 @@ class PipelinedPerception:
         assert self.inflight < len(self.slots), "collect() a finished step before submitting another one"
         i = self.head
         sl = self.slots[i]
-        S = self.model.receptive_field
-        host = self.model.prepare_inputs(intrinsics, extrinsics, future_egomotion)
         compute = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_in):
             self.copy_in.wait_event(self.ev_done[i])          # the slot's previous replay has consumed its inputs
-            for k, v in host.items():
-                sl.pinned[k].copy_(v)
-                sl.static[k].copy_(sl.pinned[k], non_blocking=True)
-            sl.static["feat"].copy_(feat[:, :S], non_blocking=True)
-            sl.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
+            sl.stage_inputs(feat, depth_logits, intrinsics, extrinsics, future_egomotion, stream=self.copy_in)
             self.ev_in[i].record(self.copy_in)
         compute.wait_event(self.ev_in[i])
         compute.wait_event(self.ev_out[i])                    # the slot's previous outputs have left the device

@@ -68,9 +68,13 @@ def _rz(yaw):
     return torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
 
 
-def camera_rig(cfg: LiftSplatConfig, batch: int, gen: torch.Generator, focal_jitter=True, random_pose=False):
+def camera_rig(cfg: LiftSplatConfig, batch: int, gen: torch.Generator, focal_jitter=True, random_pose=False,
+               tilt_deg: float = 0.0):
     """intrinsics (B,S,N,3,3), extrinsics (B,S,N,4,4) fp32.  Ring of level pinhole cameras:
-    yaw = 2*pi*n/N, position (1.5cos, 1.5sin, 1.5) m, camera z -> ego forward."""
+    yaw = 2*pi*n/N, position (1.5cos, 1.5sin, 1.5) m, camera z -> ego forward.
+    tilt_deg > 0: every camera of every sample gets a fixed (same for all frames, like a real calibration) random
+    roll / pitch / yaw error, each U[-tilt_deg, tilt_deg] degrees -- nuScenes calibrations are about 1 degree off
+    level, which is what decides how many frustum points of an image column share a BEV pillar."""
     S, N = cfg.receptive_field, cfg.n_cameras
     H, W = cfg.final_dim
     cam2ego_axes = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]], dtype=torch.float64)
@@ -90,6 +94,14 @@ def camera_rig(cfg: LiftSplatConfig, batch: int, gen: torch.Generator, focal_jit
     intr[..., 0, 2] = W / 2.0
     intr[..., 1, 2] = H / 2.0
     intr[..., 2, 2] = 1.0
+    if tilt_deg > 0.0:
+        ang = (torch.rand(batch, N, 3, generator=gen, dtype=torch.float64) - 0.5) * 2.0 * math.radians(tilt_deg)
+        for b in range(batch):
+            for n in range(N):
+                ax, ay, az = ang[b, n].tolist()
+                Rx = torch.tensor([[1, 0, 0], [0, math.cos(ax), -math.sin(ax)], [0, math.sin(ax), math.cos(ax)]], dtype=torch.float64)
+                Ry = torch.tensor([[math.cos(ay), 0, math.sin(ay)], [0, 1, 0], [-math.sin(ay), 0, math.cos(ay)]], dtype=torch.float64)
+                extr[b, :, n, :3, :3] = _rz(az) @ Ry @ Rx @ extr[b, :, n, :3, :3]
     if random_pose:  # perturb every camera by a random small rotation + offset (property tests)
         ang = (torch.rand(batch, S, N, 3, generator=gen, dtype=torch.float64) - 0.5) * 0.6
         for idx in torch.cartesian_prod(torch.arange(batch), torch.arange(S), torch.arange(N)):
@@ -117,7 +129,8 @@ def exact_gauss(shape, gen: torch.Generator) -> torch.Tensor:
     return (s - (1 << 15)).float() / float(1 << 13)
 
 
-def lift_inputs(cfg: LiftSplatConfig, batch: int, seed: int = 0, focal_jitter=True, random_pose=False):
+def lift_inputs(cfg: LiftSplatConfig, batch: int, seed: int = 0, focal_jitter=True, random_pose=False,
+                tilt_deg: float = 0.0):
     """Everything the lift-splat consumes, entering at the encoder's outputs:
       feat (B,S,N,C,Hf,Wf) = relu(randn)   (UpsamplingConcat ends in ReLU, convolutions.py:195)
       depth_logits (B,S,N,D,Hf,Wf) = 2*randn
@@ -128,10 +141,17 @@ def lift_inputs(cfg: LiftSplatConfig, batch: int, seed: int = 0, focal_jitter=Tr
     D = cfg.n_depth
     feat = exact_gauss((batch, S, N, C, Hf, Wf), gen).relu_()
     depth = exact_gauss((batch, S, N, D, Hf, Wf), gen) * 2.0
-    intr, extr = camera_rig(cfg, batch, gen, focal_jitter=focal_jitter, random_pose=random_pose)
+    intr, extr = camera_rig(cfg, batch, gen, focal_jitter=focal_jitter, random_pose=random_pose, tilt_deg=tilt_deg)
     ego = egomotion(cfg, batch, gen)
     return {"feat": feat, "depth_logits": depth, "intrinsics": intr, "extrinsics": extr,
             "future_egomotion": ego}
+
+
+def stack_samples(cfg: LiftSplatConfig, seeds, **kw):
+    """A batch assembled from single-sample draws: sample i == lift_inputs(cfg, 1, seed=seeds[i]).  Parity fixtures
+    are recorded per sample seed, so any batch built this way can be checked sample by sample."""
+    parts = [lift_inputs(cfg, 1, seed=int(s), **kw) for s in seeds]
+    return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
 
 
 def init_exact(module, seed=0):

@@ -22,9 +22,23 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "bev_frames_per_sec" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified reference package (baseline/_ref or /root/reference); "port" only where neither exists
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["samples_per_gpu_per_step"] == 4
+
+
+def test_reference_arm_uses_the_installed_reference_when_present():
+    """baseline/_ref (oracle/build_ref.py) or /root/reference present -> the arm times the reference's own modules."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        import pytest
+        pytest.skip("no reference install on this machine")
+    r = run("--impl", "reference", "--workload", "lift_splat", "--steps", "1", "--warmup", "0")
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["kind"] == "reference"
 
 
 def test_b200_arm_has_no_cpu_fallback():
