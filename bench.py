@@ -33,18 +33,21 @@ from stp3_b200.utils import synthetic as syn  # noqa: E402
 METRIC = "bev_frames_per_sec"
 UNIT = "frames/s"
 # SURVEY.md §8d / BASELINE.md §3: 2*MAC, unpadded channels, counted on the reference modules
-GFLOP_TEMPORAL, GFLOP_DECODER = 134.7, 59.3
+GFLOP_TEMPORAL, GFLOP_DECODER, GFLOP_HEADS = 134.7, 59.3, 27.4
 WORKLOADS = {
     "perceive": "perceive: 6 cam x 3 t x (28x60x48 frustum) -> lift-splat -> ego-warp + 3-D temporal block + DeepLab "
                 "head -> BEV decoder heads (seg/ped/hdmap), 200x200x64 BEV (BASELINE configs[3]; EfficientNet trunk "
                 "excluded on both arms)",
+    "perceive_heads": "perceive_heads: trunk endpoints r3 (18x56x28x60) + r4 (18x160x14x30) per sample -> encoder heads "
+                      "(DeepLabHead + UpsamplingConcat, features + depth logits) -> lift-splat (channels-last hand-off) -> "
+                      "temporal block + DeepLab head -> decoder heads; perceive (BASELINE configs[3]) plus SURVEY.md row f1",
     "lift_splat": "lift_splat: 6 cam x 3 t x (28x60x48 frustum) -> 200x200x64 BEV, ego-warp + discount "
                   "(BASELINE configs[2] lift-splat stage)",
     "stress": "stress: 6 cam x 5 t x (28x60x96 frustum), C=128 -> lift-splat -> 4 temporal blocks + DeepLab head -> BEV "
               "decoder heads, 400x400 BEV (BASELINE configs[4]; a robustness / maximum-size run, not the headline metric)",
 }
 # the whole perception path runs for these workloads (the others stop after the lift-splat)
-PERCEPTION = ("perceive", "stress")
+PERCEPTION = ("perceive", "stress", "perceive_heads")
 
 
 def algorithmic_bytes_lift_splat(cfg, batch):
@@ -111,6 +114,19 @@ class ClockSampler:
         os.unlink(self.path)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def trunk_endpoints(cfg, batch, seed):
+    """Synthetic outputs of the (third-party, excluded) EfficientNet-b4 trunk: r3 (B,S,N,56,Hf,Wf), r4 (B,S,N,160,Hf/2,Wf/2),
+    per-sample seeded like the other inputs."""
+    Hf, Wf = cfg.feat_hw
+    S, N = cfg.receptive_field, cfg.n_cameras
+    r_lo, r_hi = [], []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(1000 + seed + i)
+        r_lo.append(syn.exact_gauss((1, S, N, 56, Hf, Wf), g))
+        r_hi.append(syn.exact_gauss((1, S, N, 160, Hf // 2, Wf // 2), g))
+    return torch.cat(r_lo), torch.cat(r_hi)
 
 
 def make_problem(cfg, batch, seed, tilt_deg=0.0):
@@ -380,6 +396,10 @@ def main():
     host = {k: inp[k].pin_memory() for k in ("feat", "depth_logits", "intrinsics", "extrinsics", "future_egomotion")}
     host_mats = [m.pin_memory() for m in prob["mats"]]
     xs, ys, ds = (a.to(dev) for a in prob["axes"])
+    heads = args.workload == "perceive_heads"
+    if heads:        # the step enters at the trunk endpoints: they take the place of (feat, depth_logits) everywhere below
+        r_lo, r_hi = trunk_endpoints(cfg, b, rank * b)
+        host["feat"], host["depth_logits"] = r_lo.pin_memory(), r_hi.pin_memory()
     d_feat, d_depth = host["feat"].to(dev), host["depth_logits"].to(dev)
     d_mats = [m.to(dev) for m in host_mats]
     X, Y = cfg.bev_xy
@@ -388,7 +408,7 @@ def main():
     graphed = None
     if perceive and not args.no_graph:
         from stp3_b200.models.stp3 import GraphedPerception
-        graphed = GraphedPerception(model, b, cfg.n_cameras, dev)
+        graphed = GraphedPerception(model, b, cfg.n_cameras, dev, entry="heads" if heads else "lift")
         graphed(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])   # fill the static inputs
     if perceive:
         host_out = {"segmentation": torch.empty((b, cfg.receptive_field, 2, X, Y)).pin_memory(),
@@ -404,7 +424,8 @@ def main():
                 graphed.graph.replay()            # inputs already resident in the graph's static buffers
                 return graphed.out
             if perceive:
-                return model.forward_features(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
+                fwd = model.forward_trunk_features if heads else model.forward_features
+                return fwd(d_feat, d_depth, inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"])
             ops.lift_splat(d_feat, d_depth, *d_mats, xs, ys, ds, prob["off"], prob["res"], prob["dim"], cfg.discount, out=out)
             return {"bev": out}
 
@@ -417,7 +438,8 @@ def main():
             elif perceive:
                 f = host["feat"].to(dev, non_blocking=True)
                 d = host["depth_logits"].to(dev, non_blocking=True)
-                res = model.forward_features(f, d, host["intrinsics"], host["extrinsics"], host["future_egomotion"])
+                fwd = model.forward_trunk_features if heads else model.forward_features
+                res = fwd(f, d, host["intrinsics"], host["extrinsics"], host["future_egomotion"])
             else:
                 f = host["feat"].to(dev, non_blocking=True)
                 d = host["depth_logits"].to(dev, non_blocking=True)
@@ -482,7 +504,7 @@ def main():
     if graphed is not None and not args.no_pipeline:
         from stp3_b200.models.stp3 import PipelinedPerception
         with torch.no_grad():
-            pipe = PipelinedPerception(model, b, cfg.n_cameras, depth=2, device=dev)
+            pipe = PipelinedPerception(model, b, cfg.n_cameras, depth=2, device=dev, entry="heads" if heads else "lift")
         e2e_ms = timed_pipelined(pipe, K)
         e2e_mode = "pipelined (depth 2): copies of steps i-1 / i+1 overlap the CUDA graph of step i"
     else:
@@ -502,12 +524,13 @@ def main():
     # per-stage device time: each stage captured as its own CUDA graph (no launch gaps), timed with CUDA events
     stage_ms = {}
     if perceive:
-        stage_ms = time_stages(model, graphed.static if graphed is not None else None, d_feat, d_depth, inp, flush, dev)
+        stage_ms = time_stages(model, graphed.static if graphed is not None else None, d_feat, d_depth, inp, flush, dev,
+                               heads=heads)
     ours, total_launches, conv_ms_prof = count_launches(step_resident, dev)
 
     # the lift-splat on both rigs (level cameras = SURVEY 8d; 1 degree of roll / pitch / yaw error per camera)
     rigs = {}
-    if not args.no_extras and args.workload != "stress":
+    if not args.no_extras and args.workload in ("perceive", "lift_splat"):
         for name, tdeg in (("level", 0.0), ("tilted_1deg", 1.0)):
             pr = make_problem(cfg, b, seed=rank * b, tilt_deg=tdeg)
             f, d = pr["inp"]["feat"].to(dev), pr["inp"]["depth_logits"].to(dev)
@@ -569,9 +592,10 @@ def main():
         line["gpu_launches"] = 2 * K * ours if ours is not None else None
         line["launches_per_step"] = {"ours": ours, "all_kernels": total_launches, "how": "torch.profiler (CUPTI), one replayed step of this run"}
         if perceive:
-            dense_ms = stage_ms.get("temporal_model", 0.0) + stage_ms.get("decoder", 0.0)
+            dense_ms = stage_ms.get("temporal_model", 0.0) + stage_ms.get("decoder", 0.0) + stage_ms.get("encoder_heads", 0.0)
             # the flop count was taken on the reference modules for the perceive configuration only
-            flops = (GFLOP_TEMPORAL + GFLOP_DECODER) * 1e9 * b if args.workload == "perceive" else None
+            flops = (GFLOP_TEMPORAL + GFLOP_DECODER + (GFLOP_HEADS if heads else 0.0)) * 1e9 * b \
+                if args.workload in ("perceive", "perceive_heads") else None
             ach = flops / (dense_ms * 1e-3) / 1e12 if flops and dense_ms > 0 else None
             line["stage_ms"] = stage_ms
             line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> family (temporal model + decoder)",
@@ -653,24 +677,33 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
             "parity_vs_unsharded": err <= 1e-4, "max_rel_err_vs_unsharded": err, "launch": "eager (Python/ctypes launches on both sides)"}
 
 
-def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
-    """GPU time of the three stages of STP3.forward_device, each replayed as its own CUDA graph."""
+def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5, heads=False):
+    """GPU time of the stages of STP3.forward_device (and the encoder heads before it), each replayed as its own CUDA graph."""
     from stp3_b200 import dense, ops
     from stp3_b200.models.stp3 import STP3  # noqa: F401
     if static is None:
         h = {k: v.to(dev) for k, v in model.prepare_inputs(inp["intrinsics"], inp["extrinsics"], inp["future_egomotion"]).items()}
-        static = dict(feat=d_feat, depth_logits=d_depth, **h)
-    B, S = static["feat"].shape[:2]
+        static = dict(**({"r_lo": d_feat, "r_hi": d_depth} if heads else {"feat": d_feat, "depth_logits": d_depth}), **h)
+    B, S = static["cam_M"].shape[:2]
     X, Y = model.bev_size
     C = model.encoder_out_channels
     off, res, dim = model._bev_host()
     planes = torch.empty((2, B, S, X, Y, C), dtype=torch.bfloat16, device=dev)
     hold = {}
 
+    def enc_heads():
+        r_lo, r_hi = static["r_lo"], static["r_hi"]
+        n = r_lo.shape[2]
+        f, d = model.encoder.heads_f32(r_lo.view(B * S * n, *r_lo.shape[3:]), r_hi.view(B * S * n, *r_hi.shape[3:]),
+                                       channels_last=True)
+        hold["feat"], hold["depth"] = f.view(B, S, n, *f.shape[1:]), d.view(B, S, n, *d.shape[1:])
+
     def lift():
-        r = ops.lift_splat(static["feat"], static["depth_logits"], static["cam_M"], static["cam_t"], static["ego_R"],
+        f = hold["feat"] if heads else static["feat"]
+        d = hold["depth"] if heads else static["depth_logits"]
+        r = ops.lift_splat(f, d, static["cam_M"], static["cam_t"], static["ego_R"],
                            static["ego_t"], *model._axes(), off, res, dim, float(model.discount), workspace=model._ws,
-                           out_hilo=planes, pool_sum=True)
+                           out_hilo=planes, pool_sum=True, feat_channels_last=heads)
         hold["sums"] = r[1].view(B * S, C)
 
     def temporal():
@@ -682,7 +715,10 @@ def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5):
 
     out = {}
     with torch.no_grad():
-        for name, fn in (("lift_splat", lift), ("temporal_model", temporal), ("decoder", decoder)):
+        stages = (("lift_splat", lift), ("temporal_model", temporal), ("decoder", decoder))
+        if heads:
+            stages = (("encoder_heads", enc_heads),) + stages
+        for name, fn in stages:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):

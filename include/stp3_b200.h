@@ -102,7 +102,8 @@ int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_l
  *                already contain it): the spatially constant branches and the ego-motion channels enter here
  *   res_hi/lo    optional residual (B*T, Ho, Wo, res_cstride), channels [res_coff, res_coff+bn)
  *   y_hi, y_lo   optional output planes (B*T, Ho, Wo, out_cstride), channels [out_coff, out_coff+bn)
- *   y_f32        optional (B*T, n_valid, Ho, Wo) fp32 in the reference's NCHW layout (final logits)
+ *   y_f32        optional (B*T, n_valid, Ho, Wo) fp32 in the reference's NCHW layout (final logits), or channels-last
+ *                (desc.f32_layout = 1)
  * taps[i] = (dt, dy, dx): input coordinate = output coordinate * stride + d (dt is not strided); coordinates
  * outside the tensor read as zero (this is the reference's zero / causal padding).
  */
@@ -143,6 +144,13 @@ typedef struct stp3_conv_desc {
   void* y2_hi;
   void* y2_lo;
   int out2_cstride, out2_coff, n_store2, relu2;
+  /* input channels [k_lo, k_hi) of the window carry data (multiples of 16; k_hi = 0: the whole window): the weights of
+     the other channels are zero, so their UMMA K steps are not issued.  k_lo must lie in the first 64-channel block and
+     k_hi in the last (narrow convolutions: 35 -> 35 channels of temporal.py:436-461 run 3 of 4 K steps, 32 -> 32 run 2). */
+  int k_lo, k_hi;
+  int f32_layout;        /* layout of y_f32: 0 = (B*T, n_valid, Ho, Wo) like the reference, 1 = channels-last (B*T, Ho, Wo,
+                            n_valid) -- what stp3_lift_splat_fwd(feat_layout = 1) fetches as ONE TMA box per tile (the encoder
+                            heads hand their context features over this way, encoder.py:88-95 -> stp3.py:216) */
 } stp3_conv_desc;
 
 /* Optional fused 1x1 "head" evaluated on the activated output tile while it is still in registers:

@@ -26,7 +26,8 @@ class ConvDesc(ctypes.Structure):
                 ("bn", _I), ("out_cstride", _I), ("out_coff", _I), ("n_store", _I), ("relu", _I), ("res_mode", _I),
                 ("res_cstride", _I), ("res_coff", _I), ("n_valid", _I), ("sigmoid", _I), ("tune_n_sub", _I), ("tune_group", _I),
                 ("n_cols", _I), ("col_sums", _V), ("col_sums_scratch", _V), ("col_sums_scratch_bytes", _SZ),
-                ("y2_hi", _V), ("y2_lo", _V), ("out2_cstride", _I), ("out2_coff", _I), ("n_store2", _I), ("relu2", _I)]
+                ("y2_hi", _V), ("y2_lo", _V), ("out2_cstride", _I), ("out2_coff", _I), ("n_store2", _I), ("relu2", _I),
+                ("k_lo", _I), ("k_hi", _I), ("f32_layout", _I)]
 
 
 class ConvHead(ctypes.Structure):

@@ -49,6 +49,8 @@ struct ConvParams {
   int kblocks;              // Cin / 64 of this convolution
   int cin_off;              // first input channel inside the (wider) input tensor, multiple of 64
   int ntaps;
+  int ks_first, ks_end;     // UMMA_K = 16 steps that carry data: [ks_first, 4) of the first K block, [0, ks_end) of the last
+                            // (channels outside are zero padding of a narrow convolution: neither multiplied nor needed)
   int n_sub;                // sub-tiles per tile: 2 (16x16 pixels, weight tiles shared) or 1 (small images: more tiles)
   // taps that share one activation load: consecutive taps with the same (dt, dx) whose dy advance by the stride read
   // the same strided rows shifted by one OUTPUT row each (the three dy taps of a 3x3; dy = -3,-1,1,3 / -2,0,2 of the
@@ -77,6 +79,7 @@ struct ConvParams {
   int vec256;               // bit 0: output rows / windows are 32-byte aligned (256-bit stores), bit 1: residual likewise
   float* out_f32;           // optional (n_img, n_valid, Ho, Wo) fp32, the reference's NCHW layout
   int n_valid, f32_coff;    // channel offset of this launch inside out_f32
+  int f32_nhwc;             // out_f32 is channels-last (n_img, Ho, Wo, n_valid): 16 channels of a pixel = two 32-byte stores
   int sigmoid;              // apply to out_f32 (instance_center head)
   int na_stages, nb_stages; // smem ring depths chosen by the host
   int b_resident;           // all weight tiles of the convolution stay in shared memory for the CTA's lifetime
@@ -317,6 +320,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           for (int kb = 0; kb < p.kblocks; ++kb) {
             wait_full(&a_full[as], aph);
             ptx::tc_fence_after();
+            const int k_begin = kb == 0 ? p.ks_first : 0, k_end = kb == p.kblocks - 1 ? p.ks_end : kBK / 16;
             const uint32_t a_hi0 = ptx::smem_u32(a_ring + (size_t)as * a_stage_bytes);
             for (int j = 0; j < gsz; ++j) {
               const int it = (tap0 + j) * p.kblocks + kb;
@@ -339,12 +343,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + sub) * S::kAccCols);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
+                  if (k < k_begin || k >= k_end) continue;                 // K steps of pure channel padding
                   const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);     // advance 16 bf16 = 32 bytes along K
+                  const uint32_t acc0 = accumulate | (uint32_t)(k > k_begin);
                   if constexpr (STACK) {
-                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc2, accumulate | (uint32_t)k);   // A_hi x [W_hi; W_lo]
+                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc2, acc0);                       // A_hi x [W_hi; W_lo]
                     mma(tmem_d, da_lo + koff, db_lo + koff, idesc, 1);                          // A_lo x W_hi
                   } else {
-                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
+                    mma(tmem_d, da_hi + koff, db_hi + koff, idesc, acc0);
                     mma(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
                     mma(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
                   }
@@ -536,7 +542,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 }
               }
             }
-            if (p.out_f32) {
+            if (p.out_f32 && p.f32_nhwc) {
+              const int c0 = p.f32_coff + cb;
+              float* dst = p.out_f32 + pix * p.n_valid + c0;
+              if (c0 + 16 <= p.n_valid && (p.n_valid & 7) == 0) {          // rows are 32-byte aligned (host checks the base)
+                ptx::st_global_v8f(dst, v);
+                ptx::st_global_v8f(dst + 8, v + 8);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i < p.n_valid) dst[i] = v[i];
+              }
+            } else if (p.out_f32) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int c = p.f32_coff + cb + i;
@@ -782,6 +799,14 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   for (int i = 0; i < d->ntaps; ++i) if (d->taps[i][0] == 0 && d->taps[i][1] == 0 && d->taps[i][2] == 0) p.skip_t = 1;
   p.tiles_x = ceil_div(d->Wo, kTileW); p.tiles_y = ceil_div(d->Ho, tile_h); p.n_sub = n_sub;
   p.stride = d->stride; p.kblocks = kblocks; p.cin_off = d->cin_off; p.ntaps = d->ntaps;
+  {
+    const int k_lo = d->k_hi > 0 ? d->k_lo : 0, k_hi = d->k_hi > 0 ? d->k_hi : d->cin;
+    STP3_CHECK_ARG(k_lo % 16 == 0 && k_hi % 16 == 0 && k_lo >= 0 && k_lo < k_hi && k_hi <= d->cin &&
+                   k_lo < kBK && k_hi > d->cin - kBK, "k_lo / k_hi: multiples of 16 inside the first / last 64-channel block");
+    p.ks_first = k_lo / 16;
+    p.ks_end = (k_hi - (kblocks - 1) * kBK) / 16;
+    STP3_CHECK_ARG(kblocks > 1 || p.ks_first < p.ks_end, "empty K range");
+  }
   p.a_plane_bytes = box_h * kTileW * kBK * 2; p.w_rows = d->bn; p.n_mma = n_mma;
   for (int i = 0; i < d->ntaps; ++i) { p.tap[i][0] = d->taps[i][0]; p.tap[i][1] = d->taps[i][1]; p.tap[i][2] = d->taps[i][2]; p.tap[i][3] = 0; }
   p.relu = d->relu; p.res_mode = d->res_mode;
@@ -800,6 +825,11 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
                    "second destination: channel window does not fit");
   }
   p.out_f32 = y_f32; p.n_valid = d->n_valid; p.sigmoid = d->sigmoid;
+  p.f32_nhwc = d->f32_layout;
+  STP3_CHECK_ARG(d->f32_layout == 0 || d->f32_layout == 1, "f32_layout must be 0 (n_img, n_valid, Ho, Wo) or 1 (n_img, Ho, Wo, n_valid)");
+  if (y_f32 && d->f32_layout == 1)
+    STP3_CHECK_ARG((reinterpret_cast<uintptr_t>(y_f32) & 31) == 0 && !d->sigmoid,
+                   "channels-last y_f32 must be 32-byte aligned (and carries no sigmoid)");
   p.img_bias_stride = d->bn;
   p.head_ko = 0; p.head_w = nullptr; p.head_b = nullptr; p.head_sigmoid_mask = 0;
   for (int k = 0; k < kMaxHeadOut; ++k) { p.head_out[k] = nullptr; p.head_img_stride[k] = 0; }

@@ -33,6 +33,12 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ void st_global_v8f(void* p, const float* v) {             // 8 consecutive floats, 32-byte aligned
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // true in exactly one (elected) lane of a converged warp.  Code guarded by it may use the uniform datapath
 // (UTCHMMA / UTMALDG / UTCBAR are uniform instructions): guarding them with `lane == 0` instead makes the compiler
 // wrap every one of them in an elect-and-retry loop (~7 SASS instructions per MMA, which throttles N=64 MMAs).

@@ -78,6 +78,8 @@ class PackedConv:
     bn: int
     cout: int
     stride: int
+    k_lo: int = 0              # input channels [k_lo, k_hi) of the window carry weights (multiples of 16)
+    k_hi: int = 0
 
 
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dilation: int = 1,
@@ -122,7 +124,11 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     packed = packed.permute(1, 3, 0, 2, 4).contiguous()              # (nt, kbs, 2, bn, 64)
     b = torch.zeros(bn, dtype=torch.float32, device=dev)
     b[:cout] = bias
-    return PackedConv(packed, b, taps, cin_p, bn, cout, stride)
+    k_lo = min(off for _, _, off in in_layout) // 16 * 16
+    k_hi = (max(off + n for _, n, off in in_layout) + 15) // 16 * 16
+    if not (k_lo < KB and k_hi > cin_p - KB):          # the kernel trims only the first / last 64-channel block
+        k_lo, k_hi = 0, cin_p
+    return PackedConv(packed, b, taps, cin_p, bn, cout, stride, k_lo, k_hi)
 
 
 # ------------------------------------------------------------------------------------------------ autotuner
@@ -168,7 +174,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
          out_hw: Optional[Tuple[int, int]] = None, n_store: int = 0, frames: Optional[Tuple[int, int]] = None,
          head: Optional[dict] = None, store: bool = True, tune: Optional[Tuple[int, int]] = None,
          col_sums: Optional[torch.Tensor] = None, out2: Optional[HL] = None, out2_coff: int = 0, n_store2: int = 0,
-         relu2: bool = False) -> Optional[HL]:
+         relu2: bool = False, out_f32_nhwc: bool = False) -> Optional[HL]:
     """y = act(conv(x[..., cin_off:cin_off+cin]) + bias [+ residual]) written into out[..., out_coff:...]; when
     img_bias (n_img, bn) is given it REPLACES the convolution's bias vector (build it with bias_table()).
     out2 (bn = 128 layers, n_store <= 64): output columns [64, 64+n_store2) go to out2[..., out2_coff:...] with activation
@@ -189,6 +195,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         d.taps[i][0], d.taps[i][1], d.taps[i][2] = dt, dy, dx
     d.bn = pc.bn
     d.n_cols = pc.cout              # weight rows / bias entries beyond cout are zero padding
+    d.k_lo, d.k_hi = pc.k_lo, pc.k_hi
     if out is None and out_f32 is None and store:
         out = HL.empty(B, T, Ho, Wo, pc.cout, x.hi.device, cp=pc.bn)
     hd = None
@@ -212,6 +219,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         d.res_cstride, d.res_coff = residual.hi.shape[-1], res_coff
         assert residual.hi.shape[:4] == (B, T, Ho, Wo)
     d.n_valid, d.sigmoid = n_valid, int(sigmoid)
+    d.f32_layout = int(out_f32_nhwc)        # out_f32 (B*T, Ho, Wo, n_valid) instead of (B*T, n_valid, Ho, Wo)
     if out2 is not None:
         assert pc.bn == 128 and out is not None and out2.hi.shape[:4] == (B, T, Ho, Wo)
         d.y2_hi, d.y2_lo = out2.hi.data_ptr(), out2.lo.data_ptr()

@@ -151,8 +151,12 @@ class UpsamplingConcat(PackedModule):
         w1, b1 = dense.fold_bn(self.conv[3].weight, self.conv[4])
         return {"c0": (w0, b0), "c1": dense.pack_conv(w1, b1)}
 
-    def forward_hl(self, coarse: dense.HL, fine_f32: torch.Tensor) -> dense.HL:
-        """coarse: HL (B,1,h,w,.) with coarse.c real channels; fine_f32: (B, Cf, 2h, 2w) fp32."""
+    def forward_hl(self, coarse: dense.HL, fine_f32: torch.Tensor, out_f32: Optional[torch.Tensor] = None,
+                   out_f32_nhwc: bool = False):
+        """coarse: HL (B,1,h,w,.) with coarse.c real channels; fine_f32: (B, Cf, 2h, 2w) fp32.
+        out_f32: optional fp32 destination written by the last convolution's epilogue instead of hi/lo planes --
+        (B, Cout, 2h, 2w) like the reference, or channels-last (B, 2h, 2w, Cout) with out_f32_nhwc (the layout the
+        lift-splat fetches as one TMA box per tile)."""
         self._require_eval()
         P = self.packed()
         cf, cc = fine_f32.shape[1], coarse.c
@@ -163,7 +167,13 @@ class UpsamplingConcat(PackedModule):
         cat = dense.from_f32(fine_f32.unsqueeze(1), cp=dense.pad_to(cf + cc))
         dense.upsample2x_add(coarse, None, cc, out=cat, out_coff=cf)
         y = dense.conv(cat, P[key], relu=True)
-        return dense.conv(y, P["c1"], relu=True)
+        if out_f32 is None:
+            return dense.conv(y, P["c1"], relu=True)
+        B = y.hi.shape[0]
+        shape = (B, *y.hi.shape[2:4], self.out_channels) if out_f32_nhwc else (B, self.out_channels, *y.hi.shape[2:4])
+        assert tuple(out_f32.shape) == shape and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        dense.conv(y, P["c1"], relu=True, out_f32=out_f32, n_valid=self.out_channels, out_f32_nhwc=out_f32_nhwc, store=False)
+        return out_f32
 
     def forward(self, x_to_upsample, x):
         y = self.forward_hl(dense.from_f32(x_to_upsample.unsqueeze(1)), x)

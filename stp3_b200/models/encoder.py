@@ -54,15 +54,30 @@ class Encoder(nn.Module):
             depth = self.depth_layer_2.forward_hl(self.depth_layer_1.forward_hl(x), r_lo)
         return feat, depth
 
-    def get_features_depth(self, x):
+    def heads_f32(self, r_lo: torch.Tensor, r_hi: torch.Tensor, channels_last: bool = False):
+        """Both heads with fp32 outputs written straight from the last convolution's epilogue: context features
+        (M,C,Hf,Wf) -- or channels-last (M,Hf,Wf,C), the layout the lift-splat kernel stages with one TMA box per tile
+         -- and depth logits (M,D,Hf,Wf) (the reference's layout: they are also a model output)."""
+        M, _, Hf, Wf = r_lo.shape
+        dev = r_lo.device
+        x = dense.from_f32(r_hi.unsqueeze(1))
+        feat = torch.empty((M, Hf, Wf, self.C) if channels_last else (M, self.C, Hf, Wf), dtype=torch.float32, device=dev)
+        self.feature_layer_2.forward_hl(self.feature_layer_1.forward_hl(x), r_lo, out_f32=feat, out_f32_nhwc=channels_last)
+        depth = None
+        if self.use_depth_distribution:
+            depth = torch.empty((M, self.D, Hf, Wf), dtype=torch.float32, device=dev)
+            self.depth_layer_2.forward_hl(self.depth_layer_1.forward_hl(x), r_lo, out_f32=depth)
+        return feat, depth
+
+    def trunk(self, x):
+        """(M,3,H,W) images -> (reduction_3 (M,c3,H/8,W/8), reduction_4 (M,c4,H/16,W/16)) (encoder.py:57-86)."""
         if hasattr(self.backbone, "_conv_stem"):
-            r_lo, r_hi = _efficientnet_endpoints(self.backbone, x)
-        else:
-            r_lo, r_hi = self.backbone(x)
-        feat, depth = self.heads_hl(r_lo, r_hi)
-        f = dense.to_f32(feat, 0, self.C).squeeze(1)
-        d = dense.to_f32(depth, 0, self.D).squeeze(1) if depth is not None else None
-        return f, d
+            return _efficientnet_endpoints(self.backbone, x)
+        return self.backbone(x)
+
+    def get_features_depth(self, x, channels_last: bool = False):
+        r_lo, r_hi = self.trunk(x)
+        return self.heads_f32(r_lo.float().contiguous(), r_hi.float().contiguous(), channels_last)
 
     def forward(self, x):
         return self.get_features_depth(x)

@@ -124,22 +124,42 @@ class STP3(nn.Module):
         S = self.receptive_field
         image = image[:, :S].contiguous()
         b, s, n = image.shape[:3]
-        feat, depth = self.encoder(image.view(b * s * n, *image.shape[3:]))
+        r_lo, r_hi = self.encoder.trunk(image.view(b * s * n, *image.shape[3:]))
+        r_lo = r_lo.float().contiguous().view(b, s, n, *r_lo.shape[1:])
+        r_hi = r_hi.float().contiguous().view(b, s, n, *r_hi.shape[1:])
+        return self.forward_trunk_features(r_lo, r_hi, intrinsics, extrinsics, future_egomotion)
+
+    def forward_trunk_features(self, r_lo, r_hi, intrinsics, extrinsics, future_egomotion):
+        """forward() entering after the (third-party) EfficientNet trunk: r_lo (B,S,N,c3,H/8,W/8), r_hi
+        (B,S,N,c4,H/16,W/16) -- the encoder heads (encoder.py:88-95) run on the tcgen05 kernels and hand their context
+        features to the lift-splat channels-last."""
+        S = self.receptive_field
+        dev = r_lo.device
+        h = {k: v.to(dev) for k, v in self.prepare_inputs(intrinsics, extrinsics, future_egomotion).items()}
+        return self.forward_heads_device(r_lo[:, :S].contiguous(), r_hi[:, :S].contiguous(), **h)
+
+    def forward_heads_device(self, r_lo, r_hi, cam_M, cam_t, ego_R, ego_t, const):
+        """Device-only: encoder heads -> forward_device (capturable in a CUDA graph)."""
+        b, s, n = r_lo.shape[:3]
+        self._mark("start_heads")
+        feat, depth = self.encoder.heads_f32(r_lo.view(b * s * n, *r_lo.shape[3:]), r_hi.view(b * s * n, *r_hi.shape[3:]),
+                                             channels_last=True)
         feat = feat.view(b, s, n, *feat.shape[1:])
         depth = depth.view(b, s, n, *depth.shape[1:]) if depth is not None else None
-        return self.forward_features(feat, depth, intrinsics, extrinsics, future_egomotion)
+        self._mark("encoder_heads")
+        return self.forward_device(feat, depth, cam_M, cam_t, ego_R, ego_t, const, feat_channels_last=True)
 
-    def forward_features(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
-        """Same as forward() but entering after the image encoder: feat (B,S,N,C,Hf,Wf), depth_logits
-        (B,S,N,D,Hf,Wf)."""
+    def forward_features(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion, feat_channels_last=False):
+        """Same as forward() but entering after the image encoder: feat (B,S,N,C,Hf,Wf) [or (B,S,N,Hf,Wf,C) with
+        feat_channels_last], depth_logits (B,S,N,D,Hf,Wf)."""
         S = self.receptive_field
         dev = feat.device
         h = {k: v.to(dev) for k, v in self.prepare_inputs(intrinsics, extrinsics, future_egomotion).items()}
         feat = feat[:, :S].contiguous()
         depth_logits = depth_logits[:, :S].contiguous() if depth_logits is not None else None
-        return self.forward_device(feat, depth_logits, **h)
+        return self.forward_device(feat, depth_logits, **h, feat_channels_last=feat_channels_last)
 
-    def forward_device(self, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, const):
+    def forward_device(self, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, const, feat_channels_last=False):
         """Device-only part of the forward pass (every argument already on the GPU; no host synchronisation, so the
         whole call can be captured in a CUDA graph -- see GraphedPerception)."""
         B, S = feat.shape[:2]
@@ -155,7 +175,7 @@ class STP3(nn.Module):
             self.temporal_model.model[0].use_pyramid_pooling
         r = ops.lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, *self._axes(), off, res, dim,
                            float(self.discount), use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
-                           workspace=self._ws, out_hilo=planes, pool_sum=use_pool)
+                           workspace=self._ws, out_hilo=planes, pool_sum=use_pool, feat_channels_last=feat_channels_last)
         sums = r[1].view(B * S, C) if use_pool else None
         x = dense.HL(planes[0], planes[1], C)
         self._mark("lift_splat")
@@ -237,22 +257,39 @@ class GraphedPerception:
         out = g(feat, depth_logits, intrinsics, extrinsics, future_egomotion)   # host or device tensors
     The returned tensors are the graph's static output buffers (overwritten by the next call)."""
 
-    def __init__(self, model: STP3, batch: int, n_cameras: int, device=None):
+    def __init__(self, model: STP3, batch: int, n_cameras: int, device=None, entry: str = "lift"):
+        """entry "lift": the step enters at the encoder outputs (feat, depth_logits), STP3.forward_features;
+        entry "heads": at the trunk endpoints (r_lo, r_hi), STP3.forward_trunk_features (encoder heads included)."""
         self.model = model
+        self.entry = entry
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         S, C, D = model.receptive_field, model.encoder_out_channels, model.depth_channels
         Hf, Wf = model.frustum.shape[1:3]
         N = n_cameras
         f32 = dict(dtype=torch.float32, device=dev)
+        if entry == "lift":
+            self.big = ("feat", "depth_logits")
+            first = {"feat": torch.zeros((batch, S, N, C, Hf, Wf), **f32),
+                     "depth_logits": torch.zeros((batch, S, N, D, Hf, Wf), **f32)}
+            self._fwd = model.forward_device
+        elif entry == "heads":
+            enc = model.encoder
+            idx = {8: 3, 16: 4}[enc.downsample]
+            c_lo, c_hi = enc.reduction_channel[idx], enc.reduction_channel[idx + 1]
+            self.big = ("r_lo", "r_hi")
+            first = {"r_lo": torch.zeros((batch, S, N, c_lo, Hf, Wf), **f32),
+                     "r_hi": torch.zeros((batch, S, N, c_hi, Hf // 2, Wf // 2), **f32)}
+            self._fwd = model.forward_heads_device
+        else:
+            raise ValueError(entry)
         self.static = {
-            "feat": torch.zeros((batch, S, N, C, Hf, Wf), **f32),
-            "depth_logits": torch.zeros((batch, S, N, D, Hf, Wf), **f32),
+            **first,
             "cam_M": torch.zeros((batch, S, N, 3, 3), **f32), "cam_t": torch.zeros((batch, S, N, 3), **f32),
             "ego_R": torch.zeros((batch, S, 3, 3), **f32), "ego_t": torch.zeros((batch, S, 3), **f32),
             "const": torch.zeros((batch * S, 6), **f32),
         }
         self.pinned = {k: torch.zeros(v.shape, dtype=torch.float32).pin_memory()
-                       for k, v in self.static.items() if k not in ("feat", "depth_logits")}
+                       for k, v in self.static.items() if k not in self.big}
         self.h2d_done = torch.cuda.Event()      # the pinned staging buffers may be rewritten once this has fired
         self.h2d_done.record(torch.cuda.current_stream(dev))
         with torch.no_grad():
@@ -260,7 +297,7 @@ class GraphedPerception:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):                      # warm-up: weight packing, workspace allocation, lazy init
-                    model.forward_device(**self.static)
+                    self._fwd(**self.static)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             # the graph bakes in the device pointers of the packed / folded weights: remember which parameter versions
@@ -270,7 +307,7 @@ class GraphedPerception:
             self._keepalive = [m.__dict__["_packed_cache"] for m in self._packed_modules]
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = model.forward_device(**self.static)
+                self.out = self._fwd(**self.static)
 
     def check_weights_unchanged(self):
         """Raises if a parameter or buffer the captured kernels read was modified (load_state_dict, optimizer step,
@@ -289,10 +326,10 @@ class GraphedPerception:
         for k, v in host.items():
             self.pinned[k].copy_(v)
             self.static[k].copy_(self.pinned[k], non_blocking=True)
-        self.h2d_done.record(stream if stream is not None else torch.cuda.current_stream(self.static["feat"].device))
+        self.h2d_done.record(stream if stream is not None else torch.cuda.current_stream(self.static["cam_M"].device))
         S = self.model.receptive_field
-        self.static["feat"].copy_(feat[:, :S], non_blocking=True)
-        self.static["depth_logits"].copy_(depth_logits[:, :S], non_blocking=True)
+        self.static[self.big[0]].copy_(feat[:, :S], non_blocking=True)          # (feat, depth_logits) or (r_lo, r_hi)
+        self.static[self.big[1]].copy_(depth_logits[:, :S], non_blocking=True)
 
     def __call__(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
         """Inputs are consumed asynchronously (pinned host tensors must stay untouched until the step has run); the
@@ -313,11 +350,11 @@ class PipelinedPerception:
     """
 
     def __init__(self, model: STP3, batch: int, n_cameras: int, depth: int = 2, device=None,
-                 keys=("segmentation", "pedestrian", "hdmap")):
+                 keys=("segmentation", "pedestrian", "hdmap"), entry: str = "lift"):
         self.model = model
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         self.dev = dev
-        self.slots = [GraphedPerception(model, batch, n_cameras, dev) for _ in range(depth)]
+        self.slots = [GraphedPerception(model, batch, n_cameras, dev, entry=entry) for _ in range(depth)]
         self.keys = [k for k in keys if self.slots[0].out.get(k) is not None]
         self.host_out = [{k: torch.empty(sl.out[k].shape, dtype=torch.float32).pin_memory() for k in self.keys}
                          for sl in self.slots]

@@ -177,3 +177,27 @@ def test_temporal_model_receptive_field_5():
         ref = TD.temporal_model(x.double(), f64(tm))
         y = tm.to(DEV)(x.to(DEV))
     close(y, ref)
+
+
+def test_encoder_forward_vs_reference_golden():
+    """The drop-in Encoder (trunk endpoint bookkeeping + feature head -> 64 channels + depth head -> 48 bins) against
+    the reference's own Encoder.get_features_depth on the same stub trunk and weights (oracle/make_golden_encoder.py):
+    the reference layout, and the channels-last hand-off to the lift-splat."""
+    from oracle.stub_trunk import StubEfficientNetB4
+    from stp3_b200.config import get_cfg
+    from stp3_b200.models.encoder import Encoder
+    g = dict(np.load(os.path.join(GOLDEN, "dense_encoder_full.npz")))
+    with torch.no_grad():
+        enc = Encoder(get_cfg().MODEL.ENCODER, D=48, backbone=StubEfficientNetB4())
+        enc = TD.init_exact(enc, seed=int(g["seed"])).eval().to(DEV)
+        img = dense_input((2, 3, 224, 480), int(g["in_seed"])).to(DEV)
+        feat, depth = enc(img)
+        close(feat, torch.from_numpy(g["feature"]))
+        close(depth, torch.from_numpy(g["depth"]))
+        feat_cl, depth2 = enc.get_features_depth(img, channels_last=True)
+        assert feat_cl.shape == (2, 28, 60, 64)
+        assert torch.equal(feat_cl.permute(0, 3, 1, 2), feat) and torch.equal(depth2, depth)
+        # the older path through hi/lo planes + layout conversion gives the same values
+        r_lo, r_hi = enc.trunk(img)
+        f_hl, d_hl = enc.heads_hl(r_lo, r_hi)
+        assert (dense.to_f32(f_hl, 0, 64).squeeze(1) - feat).abs().max() <= 2e-5 * feat.abs().max()
