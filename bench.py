@@ -242,6 +242,8 @@ class ReferenceArm:
             sweep[n] = time.perf_counter() - t0
             if sweep[n] < best_t:
                 best, best_t = n, sweep[n]
+            elif sweep[n] > 1.5 * best_t:        # oversubscribed: more threads only get slower (128 threads: 20x)
+                break
         torch.set_num_threads(best)
         return best, sweep
 

@@ -84,6 +84,24 @@ int stp3_lift_splat_fwd(const float* feat, int feat_layout, const float* depth_l
                         void* workspace, size_t workspace_bytes,
                         float* out, int out_layout, void* stream);
 
+/* Backward of stp3_lift_splat_fwd (training through the drop-in): given grad_out = dLoss/d out
+ * (B,S,C,nx,ny) fp32 it returns grad_feat (B,S,N,C,Hf,Wf) and grad_depth_logits (B,S,N,D,Hf,Wf; may be NULL, and is not
+ * written when use_depth_distribution == 0).  Replaces the autograd chain of the reference:
+ *   VoxelsSumming.backward                 stp3/utils/geometry.py:321-330  (every point receives its pillar's gradient)
+ *   projection_to_birds_eye_view           stp3/models/stp3.py:239-296     (mask, index_put, bev = bev*discount + tmp)
+ *   outer product + softmax over depth     stp3/models/stp3.py:214-216
+ * Voxel indices are recomputed with the forward's exact arithmetic (not differentiable, like the reference's .long()).
+ * feat is NCHW (feat_layout 0).  scratch: stp3_lift_splat_bwd_scratch_bytes() bytes of device memory (no invariant).
+ * Gathers only, no atomics: deterministic. */
+size_t stp3_lift_splat_bwd_scratch_bytes(int B, int S, int C, int nx, int ny);
+int stp3_lift_splat_bwd(const float* grad_out, const float* feat, const float* depth_logits,
+                        const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                        const float* xs, const float* ys, const float* ds,
+                        const float* bev_off /*host[3]*/, const float* bev_res /*host[3]*/,
+                        int nx, int ny, int nz, float discount,
+                        int B, int S, int N, int D, int Hf, int Wf, int C, int use_depth_distribution,
+                        void* scratch, size_t scratch_bytes, float* grad_feat, float* grad_depth_logits, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Dense layers: implicit-GEMM convolution on tcgen05 tensor cores (TMEM accumulators, TMA-fed operands).
  *

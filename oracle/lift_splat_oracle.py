@@ -190,3 +190,37 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, off, 
             acc = acc * np.float64(F32(discount)) + splat_frame(feat[b, t], prob[b, t], rank[t], X * Y * Z)
             bev[b, t] = acc.reshape(C, X, Y)
     return {"bev": bev, "rank": ranks, "geom": geoms}
+
+
+# ----------------------------------------------------------------------------- backward
+def lift_splat_backward(grad_bev, feat, depth_logits, rank, discount, use_depth_distribution=True):
+    """fp64 gradients of loss w.r.t. feat and depth_logits given grad_bev = dloss/dbev (B,S,C,X,Y), restating the
+    reference's autograd chain:
+      discount recurrence bev[t] = bev[t-1]*discount + splat[t]   (stp3.py:296)  -> g_splat[t'] = sum_{t>=t'} discount^(t-t') g_bev[t]
+      index_put / mask / sort / VoxelsSumming.backward            (stp3.py:239-295, geometry.py:321-330): every kept point
+                                                                  receives the gradient row of its pillar, masked points zero
+      outer product x = prob (x) feat                             (stp3.py:216)
+      softmax over depth                                          (stp3.py:215)
+    rank (B,S,N,D,Hf,Wf): pillar of every point, -1 = masked (from lift_splat())."""
+    B, S, N, C, Hf, Wf = feat.shape
+    nvox = grad_bev.shape[-1] * grad_bev.shape[-2]
+    g = grad_bev.astype(np.float64).reshape(B, S, C, nvox)
+    disc = np.float64(F32(discount))
+    gs = np.zeros_like(g)
+    for t in range(S - 1, -1, -1):
+        gs[:, t] = g[:, t] + (gs[:, t + 1] * disc if t + 1 < S else 0.0)
+    prob = softmax_depth(depth_logits) if use_depth_distribution else np.ones(rank.shape, dtype=np.float64)
+    f64 = feat.astype(np.float64)
+    g_feat = np.zeros(feat.shape, dtype=np.float64)
+    g_prob = np.zeros(rank.shape, dtype=np.float64)
+    for b in range(B):
+        for t in range(S):
+            r = rank[b, t]                                          # (N,D,Hf,Wf)
+            keep = r >= 0
+            gp = np.where(keep[None], gs[b, t][:, np.where(keep, r, 0)], 0.0)      # (C,N,D,Hf,Wf) gradient of every point
+            g_feat[b, t] = np.einsum('cndhw,ndhw->nchw', gp, prob[b, t])
+            g_prob[b, t] = np.einsum('cndhw,nchw->ndhw', gp, f64[b, t])
+    if not use_depth_distribution:
+        return g_feat, None
+    dot = (prob * g_prob).sum(axis=-3, keepdims=True)
+    return g_feat, prob * (g_prob - dot)

