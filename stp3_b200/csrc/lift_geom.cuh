@@ -38,6 +38,16 @@ __device__ __forceinline__ int quantise_rank(const BevQuant& q, float x, float y
   return (int)qx * (q.ny * q.nz) + (int)qy * q.nz + (int)qz;      // cvt.rzi == .long()
 }
 
+// the same when all three resolutions are powers of two (the reference's 0.5 m grids): the divisions are exact scalings
+__device__ __forceinline__ int quantise_rank_pow2(const BevQuant& q, float x, float y, float z) {
+  const float qx = __fmul_rn(__fsub_rn(x, q.off[0]), q.inv[0]);
+  const float qy = __fmul_rn(__fsub_rn(y, q.off[1]), q.inv[1]);
+  const float qz = __fmul_rn(__fsub_rn(z, q.off[2]), q.inv[2]);
+  const bool keep = (qx > -1.f) && (qx < (float)q.nx) && (qy > -1.f) && (qy < (float)q.ny) && (qz > -1.f) && (qz < (float)q.nz);
+  if (!keep) return -1;
+  return (int)qx * (q.ny * q.nz) + (int)qy * q.nz + (int)qz;
+}
+
 // rank of the frustum point (pixel u = xw, v = yh, depth dep): camera transform `cam` (9 + 3 floats), then n_chain
 // ego-motion links `chain` (12 floats each), sequential and rounded at every step (stp3.py:270-277)
 __device__ __forceinline__ int lifted_point_rank(const BevQuant& q, const float* __restrict__ cam,

@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "lift_geom.cuh"
 #include "ptx.cuh"
 
 namespace stp3 {
@@ -60,16 +61,6 @@ struct LiftSplatParams {
   unsigned char* occ;   // (B,S,nx*ny*nz) bytes, all-zero on entry; set to 1 where the grid was written
 };
 
-// ((m0*x + m1*y) + m2*z) + t, every product and sum rounded to fp32 separately: bit-identical to the reference's
-// CPU batched 3x3 matmul followed by `+= translation` (stp3.py:197-198, 273-277).
-__device__ __forceinline__ void affine_exact(const float* __restrict__ m, const float* __restrict__ t,
-                                             float& x, float& y, float& z) {
-  const float ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), t[0]);
-  const float oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[3], x), __fmul_rn(m[4], y)), __fmul_rn(m[5], z)), t[1]);
-  const float oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[6], x), __fmul_rn(m[7], y)), __fmul_rn(m[8], z)), t[2]);
-  x = ox; y = oy; z = oz;
-}
-
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
@@ -87,6 +78,24 @@ __device__ __forceinline__ void flush_segment(float* gbase, unsigned char* obase
     else { atomicAdd(dst, a0); if (c + 1 < C) atomicAdd(dst + 1, a1); }
   }
   if (mark) obase[rank] = 1;
+}
+
+// Tensor-core pooling (phase C of the TMA kernel).  For one image column the pooled rows of all depth bins are a small
+// GEMM  out[d, c] = sum_h prob[d, h] * feat[h, c]  (M = D, K = Hf, N = C) whenever the points of a (depth, column) pair
+// fall into one pillar -- every pair of a level camera, about half of them one degree off level.  It runs on the
+// warp-level tensor-core path (mma.sync.m16n8k16, bf16 operands, fp32 accumulate) with both operands split into bf16
+// hi + lo and the three products hi*hi + hi*lo + lo*hi, i.e. ~16 significand bits per operand like the hi/lo planes the
+// BEV grid is stored in downstream.  A pair whose points fall into TWO pillars takes a second pass with the operand
+// masked to the second pillar; anything beyond that is left to a scalar segmented walk.
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = ptx::pack_bf16x2(x0, x1);
+  lo = ptx::pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
+}
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // TW = image columns per CTA (compile time so that tile indexing is shifts and immediates).
@@ -351,6 +360,36 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 //                  rows of lift_splat_scatter_kernel instead -- equally asynchronous, no registers involved
 constexpr int kTmaTW = 4;
 
+// Pillar ranks of the depth bins [da, db) of one pixel's ray, bit-exact with the reference (lift_geom.cuh).  NC ego-motion
+// links (0, 1, 2) are compile-time and live in registers with the camera transform; NC = 3: two in registers, the rest of a
+// longer chain walks the shared-memory copies.  POW2: all three grid resolutions are powers of two.
+template <int NC, bool POW2>
+__device__ __forceinline__ void ray_ranks(const BevQuant& q, const float* __restrict__ s_mat, const float* __restrict__ s_ds,
+                                          int n_chain, int da, int db, float xw, float yh, int* __restrict__ rrow,
+                                          int rstride, int32_t* __restrict__ rout, size_t ostride) {
+  float cm[12], e0[12], e1[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    cm[i] = s_mat[i];
+    e0[i] = NC > 0 ? s_mat[12 + i] : 0.f;
+    e1[i] = NC > 1 ? s_mat[24 + i] : 0.f;
+  }
+  for (int d = da; d < db; ++d) {
+    const float dep = s_ds[d];
+    float x = __fmul_rn(xw, dep);                  // stp3.py:195: (u*d, v*d, d)
+    float y = __fmul_rn(yh, dep);
+    float z = dep;
+    affine_exact(cm, cm + 9, x, y, z);             // stp3.py:196-198
+    if (NC > 0) affine_exact(e0, e0 + 9, x, y, z); // stp3.py:270-277, sequential, rounded every step
+    if (NC > 1) affine_exact(e1, e1 + 9, x, y, z);
+    if (NC > 2)
+      for (int k = 2; k < n_chain; ++k) affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
+    const int rank = POW2 ? quantise_rank_pow2(q, x, y, z) : quantise_rank(q, x, y, z);   // stp3.py:287-289, 239-255
+    if (rout) rout[(size_t)d * ostride] = rank;
+    rrow[d * rstride] = rank;
+  }
+}
+
 struct LiftSplatTmaMaps {
   CUtensorMap depth;   // (Wf, Hf, D * n_img) fp32
   CUtensorMap feat;    // NCHW: (Wf, Hf, C * n_img) fp32 ; NHWC: (C, Wf, Hf * n_img) fp32
@@ -377,8 +416,11 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   float* s_feat = s_stage + ((D * npix + 31) & ~31);               // feature tile (TMA destination)
   float* s_prob = s_feat + ((feat_floats + 31) & ~31);             // [D][TW][HP]
   int* s_rank = reinterpret_cast<int*>(s_prob + D * TW * HP);      // [D][TW][HP]
-  int* s_col = s_rank + D * TW * HP;                               // [D][TW]
-  float* s_mat = reinterpret_cast<float*>(s_col + D * TW);         // camera 12 + (kMaxFrames-1) * 12 pose floats
+  int* s_seg0 = s_rank + D * TW * HP;                              // [D][TW] first pillar of the (depth, column) pair, -1 = none
+  int* s_seg1 = s_seg0 + D * TW;                                   // [D][TW] second pillar, -1 = none
+  int* s_nseg = s_seg1 + D * TW;                                   // [D][TW] distinct pillars: 0, 1, 2, 3 (= three or more)
+  int* s_cinfo = s_nseg + D * TW;                                  // [TW] max of s_nseg over the column's depth bins
+  float* s_mat = reinterpret_cast<float*>(s_cinfo + TW);           // camera 12 + (kMaxFrames-1) * 12 pose floats
   float* s_ys = s_mat + 12 * kMaxFrames;
   float* s_ds = s_ys + Hf;
   float* s_red = s_ds + D;                                         // [blockDim]
@@ -423,8 +465,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
           const int w = w0 + wl;
           if (w < Wf) {
             const float* src = p.feat + (((size_t)img * C + c0) * Hf + h) * Wf + w;
-            for (int cl = my_part; cl < kCChunk; cl += parts)
-              cp_async_4(s_feat + feat_row(cl) * fstride + px, src + (size_t)cl * Hf * Wf);
+            for (int cl = my_part; cl < kCChunk; cl += parts)      // row = channel: conflict-free mma B-fragment loads
+              cp_async_4(s_feat + cl * fstride + px, src + (size_t)cl * Hf * Wf);
           }
         }
       }
@@ -457,9 +499,11 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   __syncthreads();
 
   // ---- phase B (pure ALU, overlaps the TMA transfers): voxel rank of every point, bit-exact with the reference
-  const float offx = p.off[0], offy = p.off[1], offz = p.off[2];
-  const float resx = p.res[0], resy = p.res[1], resz = p.res[2];
-  const float fnx = (float)p.nx, fny = (float)p.ny, fnz = (float)p.nz;
+  BevQuant bq;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { bq.off[i] = p.off[i]; bq.res[i] = p.res[i]; bq.inv[i] = p.inv[i]; bq.inv_ok[i] = p.inv_ok[i]; }
+  bq.nx = p.nx; bq.ny = p.ny; bq.nz = p.nz;
+  const bool pow2 = p.inv_ok[0] && p.inv_ok[1] && p.inv_ok[2];
   for (int px0 = 0; px0 < npix; px0 += (parts == 1 ? nthr : npix_r)) {
     const int px = px0 + (parts == 1 ? tid : tid % npix_r);
     const bool act = px < npix && my_part < parts;
@@ -471,43 +515,22 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
     int* rrow = s_rank + wl * HP + h;
     const float xw = inb ? __ldg(p.xs + w) : 0.f;
     const float yh = s_ys[h];
-    // loop invariants in registers: the camera transform, up to two ego-motion links (longer chains walk the
-    // shared-memory copies), the quantisation constants
-    float cm[12], e0[12], e1[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      cm[i] = s_mat[i];
-      e0[i] = n_chain > 0 ? s_mat[12 + i] : 0.f;
-      e1[i] = n_chain > 1 ? s_mat[24 + i] : 0.f;
-    }
-    const bool ivx = p.inv_ok[0] != 0, ivy = p.inv_ok[1] != 0, ivz = p.inv_ok[2] != 0;
-    const float inx = p.inv[0], iny = p.inv[1], inz = p.inv[2];
-    const int nyz = p.ny * p.nz, nzz = p.nz;
     int32_t* rout = p.ranks_out ? p.ranks_out + ((size_t)img * D * Hf + h) * Wf + w : nullptr;
-    for (int d = da; d < db; ++d) {
-      int rank = -1;
-      if (inb) {
-        const float dep = s_ds[d];
-        float x = __fmul_rn(xw, dep);                  // stp3.py:195: (u*d, v*d, d)
-        float y = __fmul_rn(yh, dep);
-        float z = dep;
-        affine_exact(cm, cm + 9, x, y, z);             // stp3.py:196-198
-        if (n_chain > 0) affine_exact(e0, e0 + 9, x, y, z);     // stp3.py:270-277, sequential, rounded every step
-        if (n_chain > 1) affine_exact(e1, e1 + 9, x, y, z);
-        for (int k = 2; k < n_chain; ++k)
-          affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
-        const float qx = ivx ? __fmul_rn(__fsub_rn(x, offx), inx) : __fdiv_rn(__fsub_rn(x, offx), resx);
-        const float qy = ivy ? __fmul_rn(__fsub_rn(y, offy), iny) : __fdiv_rn(__fsub_rn(y, offy), resy);
-        const float qz = ivz ? __fmul_rn(__fsub_rn(z, offz), inz) : __fdiv_rn(__fsub_rn(z, offz), resz);
-        const bool keep = (qx > -1.f) && (qx < fnx) && (qy > -1.f) && (qy < fny) && (qz > -1.f) && (qz < fnz);
-        if (keep) {
-          const int ix = (int)qx, iy = (int)qy, iz = (int)qz;     // cvt.rzi == .long() truncation
-          rank = ix * nyz + iy * nzz + iz;                         // stp3.py:251-255
-        }
-        if (rout) rout[(size_t)d * Hf * Wf] = rank;
-      }
-      rrow[d * TW * HP] = rank;
+    if (!inb) {
+      for (int d = da; d < db; ++d) rrow[d * TW * HP] = -1;
+      continue;
     }
+    const size_t ost = (size_t)Hf * Wf;
+#define STP3_RAY(NC_)                                                                                             \
+    do {                                                                                                          \
+      if (pow2) ray_ranks<NC_, true>(bq, s_mat, s_ds, n_chain, da, db, xw, yh, rrow, TW * HP, rout, ost);            \
+      else ray_ranks<NC_, false>(bq, s_mat, s_ds, n_chain, da, db, xw, yh, rrow, TW * HP, rout, ost);                \
+    } while (0)
+    if (n_chain == 0) STP3_RAY(0);
+    else if (n_chain == 1) STP3_RAY(1);
+    else if (n_chain == 2) STP3_RAY(2);
+    else STP3_RAY(3);
+#undef STP3_RAY
   }
   __syncthreads();
 
@@ -550,27 +573,37 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
     }
   }
   __syncthreads();
-  for (int i = tid; i < D * TW; i += nthr) {       // column summary: one thread per (d, wl)
+  if (tid < TW) s_cinfo[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < D * TW; i += nthr) {       // summary of every (depth, column) pair: its first two pillars
     const int* r = s_rank + i * HP;
-    int first = -1;
-    bool uni = true;
+    int r0 = -1, r1 = -1, n = 0;
     for (int h = 0; h < Hf; ++h) {
       const int v = r[h];
-      if (v >= 0) { uni &= (first < 0 || v == first); first = v; }
+      if (v >= 0 && v != r0 && v != r1) {
+        if (n == 0) r0 = v; else if (n == 1) r1 = v;
+        n = min(n + 1, 3);
+      }
     }
-    s_col[i] = uni ? first : -2;
+    s_seg0[i] = r0; s_seg1[i] = r1; s_nseg[i] = n;  // masked rows carry probability 0: they never split a pair
+    if (n > 0) atomicMax(&s_cinfo[i % TW], n);
   }
   __syncthreads();
 
-  // ---- phase C: outer product + segmented pooling (see lift_splat_scatter_kernel)
+  // ---- phase C: pooling on the tensor cores (see split_bf16x2 / mma_bf16_m16n8k16 above).
+  // warp = (image column wl, half of the 64 channels); per m-tile of 16 depth bins: A = probabilities masked to the
+  // pass's pillar (16 x Hf), B = the column's features (Hf x 32 channels, fragments loaded once per channel chunk),
+  // accumulators flushed with one red.global.add.v2.f32 per lane and (depth bin, 8-channel group).
   const int warp = tid >> 5, lane = tid & 31;
-  const int nwarps = nthr >> 5;
-  const int dsplit = max(1, nwarps / TW);
-  const int dper = (D + dsplit - 1) / dsplit;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wl = warp & (TW - 1), nhalf = warp / TW;            // 8 warps: 4 columns x 2 channel halves
   const size_t nvox = (size_t)p.nx * p.ny * p.nz;
   float* gbase = p.grid + (size_t)bt * nvox * C;
   unsigned char* obase = p.occ + (size_t)bt * nvox;
-  const bool vec_ok = (C % 2) == 0;
+  constexpr int KS = 2;                                          // k-steps of 16 image rows: Hf <= 32 (host-checked)
+  const int n_mt = (D + 15) >> 4;
+  const bool col_ok = w0 + wl < Wf;
+  const int cmax = s_cinfo[wl];                                  // 0: nothing of this column lands in the grid
   uint32_t fphase = 0;
   for (int c0 = 0; c0 < C; c0 += kCChunk) {
     if (p.feat_nhwc) {
@@ -580,65 +613,108 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
       cp_async_commit_wait_all();
       __syncthreads();
     }
-    const int c = c0 + 2 * lane;
-    const bool mark = (lane == 0) && (c0 == 0);
-    for (int item = warp; item < TW * dsplit; item += nwarps) {
-      const int wl = item % TW;
-      if (w0 + wl >= Wf) continue;
-      const int d0 = (item / TW) * dper;
-      const int d1 = min(D, d0 + dper);
-      for (int h0 = 0; h0 < Hf; h0 += kHChunk) {
-        float f0[kHChunk], f1[kHChunk];
+    if (col_ok && cmax > 0) {
+      // B fragments: b0 = (k = 2tg, 2tg+1; n = g), b1 = (k = 2tg+8, 2tg+9; n = g) of every 16 x 8 block
+      uint32_t bh[4][KS][2], bl[4][KS][2];
 #pragma unroll
-        for (int j = 0; j < kHChunk; ++j) {
-          const int h = h0 + j;
-          f0[j] = 0.f; f1[j] = 0.f;
-          if (h < Hf) {
+      for (int nt = 0; nt < 4; ++nt) {
+        const int cl = nhalf * 32 + nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int h = ks * 16 + r * 8 + 2 * tg;
+            float x0 = 0.f, x1 = 0.f;
             if (p.feat_nhwc) {
-              const float2 v = *reinterpret_cast<const float2*>(s_feat + (h * TW + wl) * kCChunk + 2 * lane);
-              f0[j] = v.x; f1[j] = v.y;
+              if (h < Hf) x0 = s_feat[(h * TW + wl) * kCChunk + cl];
+              if (h + 1 < Hf) x1 = s_feat[((h + 1) * TW + wl) * kCChunk + cl];
             } else {
-              f0[j] = s_feat[lane * fstride + h * TW + wl];
-              f1[j] = s_feat[(lane + 32) * fstride + h * TW + wl];
+              if (h < Hf) x0 = s_feat[cl * fstride + h * TW + wl];
+              if (h + 1 < Hf) x1 = s_feat[cl * fstride + (h + 1) * TW + wl];
             }
+            split_bf16x2(x0, x1, bh[nt][ks][r], bl[nt][ks][r]);
           }
         }
-        for (int d = d0; d < d1; ++d) {
-          const int col = s_col[d * TW + wl];
-          if (col == -1) continue;                   // the whole column is outside the grid
-          const float* pr = s_prob + (d * TW + wl) * HP + h0;
-          if (col >= 0) {
-            float a0 = 0.f, a1 = 0.f;
+      }
+      const int n_pass = min(cmax, 2);
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int* seg = pass == 0 ? s_seg0 : s_seg1;
+        for (int mt = 0; mt < n_mt; ++mt) {
+          const int d_lo = mt * 16 + g, d_hi = d_lo + 8;
+          const int seg_lo = d_lo < D ? seg[d_lo * TW + wl] : -1;
+          const int seg_hi = d_hi < D ? seg[d_hi * TW + wl] : -1;
+          if (__ballot_sync(0xffffffffu, (seg_lo >= 0) || (seg_hi >= 0)) == 0u) continue;
+          // A fragments: a0 = (row g, k = 2tg, 2tg+1), a1 = (row g+8, same k), a2 / a3 = the same rows at k + 8
+          uint32_t ah[KS][4], al[KS][4];
 #pragma unroll
-            for (int j4 = 0; j4 < kHChunk / 4; ++j4) {
-              if (h0 + 4 * j4 < Hf) {
-                const float4 q = *reinterpret_cast<const float4*>(pr + 4 * j4);
-                a0 = fmaf(q.x, f0[4 * j4 + 0], a0); a1 = fmaf(q.x, f1[4 * j4 + 0], a1);
-                a0 = fmaf(q.y, f0[4 * j4 + 1], a0); a1 = fmaf(q.y, f1[4 * j4 + 1], a1);
-                a0 = fmaf(q.z, f0[4 * j4 + 2], a0); a1 = fmaf(q.z, f1[4 * j4 + 2], a1);
-                a0 = fmaf(q.w, f0[4 * j4 + 3], a0); a1 = fmaf(q.w, f1[4 * j4 + 3], a1);
-              }
-            }
-            flush_segment(gbase, obase, col, C, c, vec_ok, mark, a0, a1);
-          } else {
-            const int* rk = s_rank + (d * TW + wl) * HP + h0;
-            int cur = -1;
-            float a0 = 0.f, a1 = 0.f;
+          for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-            for (int j = 0; j < kHChunk; ++j) {
-              if (h0 + j < Hf) {
-                const int r = rk[j];
-                if (r != cur) {
-                  if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
-                  cur = r; a0 = 0.f; a1 = 0.f;
-                }
-                const float q = pr[j];
-                a0 = fmaf(q, f0[j], a0);
-                a1 = fmaf(q, f1[j], a1);
+            for (int r = 0; r < 4; ++r) {
+              const int h = ks * 16 + (r >> 1) * 8 + 2 * tg;
+              const int sg = (r & 1) ? seg_hi : seg_lo;
+              const int d = (r & 1) ? d_hi : d_lo;
+              float x0 = 0.f, x1 = 0.f;
+              if (sg >= 0 && h < HP) {
+                const float2 q = *reinterpret_cast<const float2*>(s_prob + (d * TW + wl) * HP + h);
+                const int2 rk = *reinterpret_cast<const int2*>(s_rank + (d * TW + wl) * HP + h);
+                x0 = rk.x == sg ? q.x : 0.f;
+                x1 = rk.y == sg ? q.y : 0.f;
               }
+              split_bf16x2(x0, x1, ah[ks][r], al[ks][r]);
             }
-            if (cur >= 0) flush_segment(gbase, obase, cur, C, c, vec_ok, mark, a0, a1);
           }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              mma_bf16_m16n8k16(acc, ah[ks], bh[nt][ks][0], bh[nt][ks][1]);
+              mma_bf16_m16n8k16(acc, ah[ks], bl[nt][ks][0], bl[nt][ks][1]);
+              mma_bf16_m16n8k16(acc, al[ks], bh[nt][ks][0], bh[nt][ks][1]);
+            }
+            // c0, c1 = (row g, columns 2tg, 2tg+1); c2, c3 = (row g+8, same columns)
+            const int c = c0 + nhalf * 32 + nt * 8 + 2 * tg;
+            if (seg_lo >= 0) red_add_v2(gbase + (size_t)seg_lo * C + c, acc[0], acc[1]);
+            if (seg_hi >= 0) red_add_v2(gbase + (size_t)seg_hi * C + c, acc[2], acc[3]);
+          }
+          if (c0 == 0 && nhalf == 0 && tg == 0) {
+            if (seg_lo >= 0) obase[seg_lo] = 1;
+            if (seg_hi >= 0) obase[seg_hi] = 1;
+          }
+        }
+      }
+      // leftovers: (depth, column) pairs that touch three or more pillars -- segmented walk over the rows that belong
+      // to neither of the two pillars the tensor-core passes covered; lanes own channel pairs, the two warps of the
+      // column split the depth bins
+      if (cmax >= 3) {
+        const int c = c0 + 2 * lane;
+        for (int d = nhalf; d < D; d += 2) {
+          if (s_nseg[d * TW + wl] < 3) continue;
+          const int e0 = s_seg0[d * TW + wl], e1 = s_seg1[d * TW + wl];
+          const int* rk = s_rank + (d * TW + wl) * HP;
+          const float* pr = s_prob + (d * TW + wl) * HP;
+          int cur = -1;
+          float a0 = 0.f, a1 = 0.f;
+          for (int h = 0; h < Hf; ++h) {
+            const int r = rk[h];
+            if (r < 0 || r == e0 || r == e1) continue;      // warp-uniform
+            if (r != cur) {
+              if (cur >= 0) flush_segment(gbase, obase, cur, C, c, true, lane == 0 && c0 == 0, a0, a1);
+              cur = r; a0 = 0.f; a1 = 0.f;
+            }
+            float f0, f1;
+            if (p.feat_nhwc) {
+              const float2 v = *reinterpret_cast<const float2*>(s_feat + (h * TW + wl) * kCChunk + 2 * lane);
+              f0 = v.x; f1 = v.y;
+            } else {
+              f0 = s_feat[(2 * lane) * fstride + h * TW + wl];
+              f1 = s_feat[(2 * lane + 1) * fstride + h * TW + wl];
+            }
+            const float q = pr[h];
+            a0 = fmaf(q, f0, a0);
+            a1 = fmaf(q, f1, a1);
+          }
+          if (cur >= 0) flush_segment(gbase, obase, cur, C, c, true, lane == 0 && c0 == 0, a0, a1);
         }
       }
     }
@@ -1042,7 +1118,7 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
   };
   // fast path: TMA-staged tiles (needs 16-byte aligned rows for the tensor maps)
   static const int no_tma = [] { const char* e = getenv("STP3_LIFT_NO_TMA"); return e ? atoi(e) : 0; }();
-  const bool tma_ok = !no_tma && TW == 4 && Wf % 4 == 0 && (feat_layout == 0 || C % 4 == 0) && D <= 256 && Hf <= 256 &&
+  const bool tma_ok = !no_tma && TW == 4 && Wf % 4 == 0 && (feat_layout == 0 || C % 4 == 0) && D <= 256 && Hf <= 32 /* two mma k-steps */ &&
                       (reinterpret_cast<uintptr_t>(feat) & 15) == 0 &&
                       (!depth_logits || (reinterpret_cast<uintptr_t>(depth_logits) & 15) == 0);
   int rc = STP3_OK;
@@ -1082,7 +1158,7 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
         const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * 4) | 1;
         const int feat_floats = feat_layout ? npix * kCChunk : kCChunk * fstride;
         const size_t smem_tma = 128 + ((size_t)((D * npix + 31) & ~31) + ((feat_floats + 31) & ~31) + 2 * (size_t)D * 4 * HP +
-                                       (size_t)D * 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
+                                       3 * (size_t)D * 4 + 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
         if (smem_tma <= 113 * 1024) {
           STP3_CUDA_OK(cudaFuncSetAttribute(lift_splat_scatter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem_tma));
