@@ -38,14 +38,19 @@ __device__ __forceinline__ int quantise_rank(const BevQuant& q, float x, float y
   return (int)qx * (q.ny * q.nz) + (int)qy * q.nz + (int)qz;      // cvt.rzi == .long()
 }
 
-// the same when all three resolutions are powers of two (the reference's 0.5 m grids): the divisions are exact scalings
-__device__ __forceinline__ int quantise_rank_pow2(const BevQuant& q, float x, float y, float z) {
+// The same for the grids the reference configures: x / y resolutions that are powers of two (0.5 m: the divisions are
+// exact scalings) and ONE height bin (nz == 1, which the kernels require anyway).  With a single bin the z index is 0 and
+// only the mask needs z: trunc(fl(a / r)) == 0  <=>  -1 < fl(a / r) < 1  <=>  -r < a < r  for a = z - off_z, r > 0 --
+// a correctly rounded quotient of two floats is below 1 exactly when the numerator is below the denominator (a <= pred(r)
+// gives a / r <= 1 - 2^-24, which is representable) -- so the true division (height resolution 20 m is not a power of
+// two) is never evaluated.
+__device__ __forceinline__ int quantise_rank_pow2xy_nz1(const BevQuant& q, float x, float y, float z) {
   const float qx = __fmul_rn(__fsub_rn(x, q.off[0]), q.inv[0]);
   const float qy = __fmul_rn(__fsub_rn(y, q.off[1]), q.inv[1]);
-  const float qz = __fmul_rn(__fsub_rn(z, q.off[2]), q.inv[2]);
-  const bool keep = (qx > -1.f) && (qx < (float)q.nx) && (qy > -1.f) && (qy < (float)q.ny) && (qz > -1.f) && (qz < (float)q.nz);
+  const float az = __fsub_rn(z, q.off[2]);
+  const bool keep = (qx > -1.f) && (qx < (float)q.nx) && (qy > -1.f) && (qy < (float)q.ny) && (az > -q.res[2]) && (az < q.res[2]);
   if (!keep) return -1;
-  return (int)qx * (q.ny * q.nz) + (int)qy * q.nz + (int)qz;
+  return (int)qx * q.ny + (int)qy;
 }
 
 // rank of the frustum point (pixel u = xw, v = yh, depth dep): camera transform `cam` (9 + 3 floats), then n_chain

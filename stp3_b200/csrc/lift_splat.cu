@@ -354,15 +354,14 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 // (cp.async.bulk.tensor, 3-D boxes) the moment the CTA starts, and the pure-ALU rank computation (phase B) runs while
 // they are in flight; nothing in the kernel waits on a global load except the two mbarrier waits.
 //   logits   box (4 w, Hf, D)      -> s_stage [D][Hf][4]            (softmax transposes it into s_prob [D][4][HP])
-//   features NHWC: 1 box (64 ch, 4 w, Hf)  -> s_feat[Hf][4][64]   (channel pairs are float2-readable, conflict free)
-//            NCHW: TMA destinations are 128-byte granular, which would force a 16-way bank conflict on the register
-//                  fill; the tile is fetched with 4-byte cp.async (LDGSTS) straight into the permuted / odd-stride
-//                  rows of lift_splat_scatter_kernel instead -- equally asynchronous, no registers involved
+//   features NHWC: 1 box (64 ch, 4 w, Hf)  -> s_feat[Hf][4][64]
+//            NCHW: 1 box (4 w, Hf, 64 ch)  -> s_feat[64][Hf][4]   (only the mma B-fragment loads of phase C read it: 64 LDS
+//                  per warp and column, so their bank conflicts do not matter)
 constexpr int kTmaTW = 4;
 
 // Pillar ranks of the depth bins [da, db) of one pixel's ray, bit-exact with the reference (lift_geom.cuh).  NC ego-motion
 // links (0, 1, 2) are compile-time and live in registers with the camera transform; NC = 3: two in registers, the rest of a
-// longer chain walks the shared-memory copies.  POW2: all three grid resolutions are powers of two.
+// longer chain walks the shared-memory copies.  POW2: x / y resolutions are powers of two and nz == 1 (lift_geom.cuh).
 template <int NC, bool POW2>
 __device__ __forceinline__ void ray_ranks(const BevQuant& q, const float* __restrict__ s_mat, const float* __restrict__ s_ds,
                                           int n_chain, int da, int db, float xw, float yh, int* __restrict__ rrow,
@@ -384,7 +383,7 @@ __device__ __forceinline__ void ray_ranks(const BevQuant& q, const float* __rest
     if (NC > 1) affine_exact(e1, e1 + 9, x, y, z);
     if (NC > 2)
       for (int k = 2; k < n_chain; ++k) affine_exact(s_mat + 12 + 12 * k, s_mat + 12 + 12 * k + 9, x, y, z);
-    const int rank = POW2 ? quantise_rank_pow2(q, x, y, z) : quantise_rank(q, x, y, z);   // stp3.py:287-289, 239-255
+    const int rank = POW2 ? quantise_rank_pow2xy_nz1(q, x, y, z) : quantise_rank(q, x, y, z);   // stp3.py:287-289, 239-255
     if (rout) rout[(size_t)d * ostride] = rank;
     rrow[d * rstride] = rank;
   }
@@ -395,13 +394,6 @@ struct LiftSplatTmaMaps {
   CUtensorMap feat;    // NCHW: (Wf, Hf, C * n_img) fp32 ; NHWC: (C, Wf, Hf * n_img) fp32
 };
 
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
 __global__ void __launch_bounds__(kScatterThreads, 2)
 lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, const LiftSplatParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -410,8 +402,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   const int D = p.D, Hf = p.Hf, Wf = p.Wf, C = p.C;
   const int HP = (Hf + 3) & ~3;
   const int npix = Hf * TW;
-  const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * TW) | 1;   // NCHW rows: odd, zero-padded to whole h-chunks
-  const int feat_floats = p.feat_nhwc ? npix * kCChunk : kCChunk * fstride;
+  const int fstride = npix;                                        // NCHW tile: [64 channels][Hf][TW]
+  const int feat_floats = npix * kCChunk;
   float* s_stage = reinterpret_cast<float*>(smem_raw);             // [D][Hf][TW] raw logits (TMA destination)
   float* s_feat = s_stage + ((D * npix + 31) & ~31);               // feature tile (TMA destination)
   float* s_prob = s_feat + ((feat_floats + 31) & ~31);             // [D][TW][HP]
@@ -450,35 +442,18 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   const int my_part = (nthr / npix_r) <= 1 ? 0 : tid / npix_r;
   const int dchunk = (D + parts - 1) / parts;
 
-  // start the feature tile of channels [c0, c0+64): NHWC = one TMA box (thread 0), NCHW = 4-byte cp.async by all
+  // start the feature tile of channels [c0, c0+64): one TMA box, issued by thread 0
   auto issue_features = [&](int c0) {
-    if (p.feat_nhwc) {
-      if (tid == 0) {
-        ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(npix * kCChunk * 4));
-        ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], c0, w0, img * Hf);
-      }
-    } else {
-      for (int px0 = 0; px0 < npix; px0 += npix_r) {
-        const int px = px0 + tid % npix_r;
-        if (px < npix && my_part < parts) {
-          const int wl = px % TW, h = px / TW;
-          const int w = w0 + wl;
-          if (w < Wf) {
-            const float* src = p.feat + (((size_t)img * C + c0) * Hf + h) * Wf + w;
-            for (int cl = my_part; cl < kCChunk; cl += parts)      // row = channel: conflict-free mma B-fragment loads
-              cp_async_4(s_feat + cl * fstride + px, src + (size_t)cl * Hf * Wf);
-          }
-        }
-      }
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[1], (uint32_t)(npix * kCChunk * 4));
+      if (p.feat_nhwc) ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], c0, w0, img * Hf);
+      else ptx::tma_load_3d(s_feat, &maps.feat, &bars[1], w0, 0, img * C + c0);
     }
   };
-  if (!p.feat_nhwc)                                       // zero padding / out-of-image columns of the NCHW rows
-    for (int i = tid; i < kCChunk * fstride; i += nthr) s_feat[i] = 0.f;
   if (tid == 0 && p.use_depth) {
     ptx::mbar_arrive_expect_tx(&bars[0], (uint32_t)(D * npix * 4));
     ptx::tma_load_3d(s_stage, &maps.depth, &bars[0], w0, 0, img * D);
   }
-  __syncthreads();                                        // zero fill complete before the async copies land
   issue_features(0);
 
   if (tid < 9) s_mat[tid] = p.cam_M[img * 9 + tid];
@@ -503,7 +478,7 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
 #pragma unroll
   for (int i = 0; i < 3; ++i) { bq.off[i] = p.off[i]; bq.res[i] = p.res[i]; bq.inv[i] = p.inv[i]; bq.inv_ok[i] = p.inv_ok[i]; }
   bq.nx = p.nx; bq.ny = p.ny; bq.nz = p.nz;
-  const bool pow2 = p.inv_ok[0] && p.inv_ok[1] && p.inv_ok[2];
+  const bool pow2 = p.inv_ok[0] && p.inv_ok[1] && p.nz == 1 && p.res[2] > 0.f;
   for (int px0 = 0; px0 < npix; px0 += (parts == 1 ? nthr : npix_r)) {
     const int px = px0 + (parts == 1 ? tid : tid % npix_r);
     const bool act = px < npix && my_part < parts;
@@ -606,13 +581,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   const int cmax = s_cinfo[wl];                                  // 0: nothing of this column lands in the grid
   uint32_t fphase = 0;
   for (int c0 = 0; c0 < C; c0 += kCChunk) {
-    if (p.feat_nhwc) {
-      ptx::mbar_wait(&bars[1], fphase);
-      fphase ^= 1;
-    } else {
-      cp_async_commit_wait_all();
-      __syncthreads();
-    }
+    ptx::mbar_wait(&bars[1], fphase);
+    fphase ^= 1;
     if (col_ok && cmax > 0) {
       // B fragments: b0 = (k = 2tg, 2tg+1; n = g), b1 = (k = 2tg+8, 2tg+9; n = g) of every 16 x 8 block
       uint32_t bh[4][KS][2], bl[4][KS][2];
@@ -1141,8 +1111,13 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
         memset(&maps.depth, 0, sizeof(maps.depth));
       }
       if (feat_layout == 0) {
-        memset(&maps.feat, 0, sizeof(maps.feat));       // NCHW features travel by cp.async, no tensor map
-        r2 = CUDA_SUCCESS;
+        const cuuint64_t dims[3] = {(cuuint64_t)Wf, (cuuint64_t)Hf, (cuuint64_t)(C * n_img)};
+        const cuuint64_t strides[2] = {(cuuint64_t)Wf * 4, (cuuint64_t)Hf * Wf * 4};
+        const cuuint32_t box[3] = {4, (cuuint32_t)Hf, (cuuint32_t)(C < kCChunk ? C : kCChunk)};
+        const cuuint32_t es[3] = {1, 1, 1};
+        r2 = enc(&maps.feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       } else {
         const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Wf, (cuuint64_t)(Hf * n_img)};
         const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)Wf * C * 4};
@@ -1155,8 +1130,7 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
       // channel chunks must be whole for the fixed-size transaction counts: C % 64 == 0 (NCHW groups of 8 / NHWC box)
       if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && C % kCChunk == 0) {
         const int HP = (Hf + 3) & ~3, npix = Hf * 4;
-        const int fstride = (((Hf + kHChunk - 1) / kHChunk) * kHChunk * 4) | 1;
-        const int feat_floats = feat_layout ? npix * kCChunk : kCChunk * fstride;
+        const int feat_floats = npix * kCChunk;
         const size_t smem_tma = 128 + ((size_t)((D * npix + 31) & ~31) + ((feat_floats + 31) & ~31) + 2 * (size_t)D * 4 * HP +
                                        3 * (size_t)D * 4 + 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
         if (smem_tma <= 113 * 1024) {
