@@ -668,6 +668,41 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
             return parallel.max_over_ranks(tot / reps, dev)
         ms_sharded = timed(lambda: model.forward_features_frame_sharded(*a))
         ms_full = timed(lambda: model.forward_features(*a))
+        # the all-gather fused into the finalize kernel's epilogue (peer stores over NVLink, symmetric memory)
+        peer = None
+        try:
+            for _ in range(3):
+                shp = model.forward_features_frame_sharded(*a, gather="peer")
+            torch.cuda.synchronize()
+            err_p = max(float((shp[k] - full[k]).abs().max() / full[k].abs().max()) for k in ("segmentation", "pedestrian", "hdmap"))
+            ms_peer = timed(lambda: model.forward_features_frame_sharded(*a, gather="peer"))
+            # the lift stage alone, both ways: splat own frames + exchange + discount
+            from stp3_b200 import ops
+            h = {k: v.to(dev) for k, v in model.prepare_inputs(a[2], a[3], a[4]).items()}
+            off, res, dim = model._bev_host()
+            f0s, fcs = parallel.shard_batch(S, rank, world)
+            pf = model.__dict__["_peer_frames"][1]
+
+            def lift_nccl():
+                r = ops.lift_splat_frames(a[0], a[1], h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *model._axes(), off, res, dim,
+                                          f0s, fcs, workspace=model._ws) if fcs > 0 else torch.empty((0, X, Y, C), device=dev)
+                ops.bev_discount(parallel.all_gather_frames(r, S).view(1, S, X, Y, C), float(model.discount))
+
+            def lift_peer():
+                pf.barrier()
+                if fcs > 0:
+                    ops.lift_splat_frames(a[0], a[1], h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *model._axes(), off, res, dim,
+                                          f0s, fcs, workspace=model._ws, peer_ptrs=pf.ptrs)
+                pf.barrier()
+                ops.bev_discount(pf.buf.view(1, S, X, Y, C), float(model.discount))
+            for _ in range(2):
+                lift_nccl(); lift_peer()
+            peer = {"ms": ms_peer, "parity_vs_unsharded": parallel.max_over_ranks(err_p, dev) <= 1e-4,
+                    "lift_stage_ms_nccl_allgather": timed(lift_nccl), "lift_stage_ms_peer_stores": timed(lift_peer),
+                    "how": "finalize epilogue stores each frame into every rank's symmetric-memory buffer (st.global on peer "
+                           "addresses), two device-side barriers, no collective launch"}
+        except Exception as e:      # no P2P / symmetric memory on this box: report, keep the NCCL numbers
+            peer = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         f0, fc = parallel.shard_batch(S, rank, world)
         raw = torch.zeros((fc, X, Y, C), dtype=torch.float32, device=dev)
         ms_ag = timed(lambda: parallel.all_gather_frames(raw, S))
@@ -676,7 +711,8 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
     return {"global_batch": 1, "frames_per_rank": [parallel.shard_batch(S, r, world)[1] for r in range(world)],
             "ms": ms_sharded, "ms_unsharded_same_sample": ms_full, "allgather_ms": ms_ag,
             "bytes": int(world * cmax * X * Y * C * 4), "bytes_note": "all_gather_into_tensor output per rank (padded to equal shards)",
-            "parity_vs_unsharded": err <= 1e-4, "max_rel_err_vs_unsharded": err, "launch": "eager (Python/ctypes launches on both sides)"}
+            "parity_vs_unsharded": err <= 1e-4, "max_rel_err_vs_unsharded": err, "launch": "eager (Python/ctypes launches on both sides)",
+            "fused_allgather": peer}
 
 
 def time_stages(model, static, d_feat, d_depth, inp, flush, dev, reps=5, heads=False):

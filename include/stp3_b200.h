@@ -240,6 +240,20 @@ int stp3_lift_splat_frames_fwd(const float* feat, int feat_layout, const float* 
                                int B, int S, int N, int D, int Hf, int Wf, int C,
                                int use_depth_distribution, int f_begin, int f_count,
                                void* workspace, size_t workspace_bytes, float* out_raw, void* stream);
+/* The same, FUSED WITH THE ALL-GATHER: the finalize epilogue stores every finished BEV row of flat frame f straight into
+ * slot f of all n_peers gathered buffers peer_out[r] (each (B*S, nx, ny, C) fp32; peer-mapped device pointers of every
+ * rank's buffer including this rank's own, e.g. from CUDA IPC / torch symmetric memory) over NVLink -- no separate
+ * collective launch.  The caller brackets the call with a cross-rank barrier on both sides (buffers free / stores
+ * landed) and then runs stp3_bev_discount on its own buffer.  peer_out is a HOST array of n_peers <= 8 pointers. */
+int stp3_lift_splat_frames_allgather_fwd(const float* feat, int feat_layout, const float* depth_logits,
+                                         const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                                         const float* xs, const float* ys, const float* ds,
+                                         const float* bev_off /*host[3]*/, const float* bev_res /*host[3]*/,
+                                         int nx, int ny, int nz,
+                                         int B, int S, int N, int D, int Hf, int Wf, int C,
+                                         int use_depth_distribution, int f_begin, int f_count,
+                                         void* workspace, size_t workspace_bytes,
+                                         int n_peers, void* const* peer_out, void* stream);
 int stp3_bev_discount(const float* raw /*(B,S,nx,ny,C) fp32*/, int B, int S, int nx, int ny, int C, float discount,
                       void* out_hi, void* out_lo /*(B,S,nx,ny,C) bf16 each*/, void* stream);
 

@@ -54,6 +54,9 @@ SIGNATURES = {
     "stp3_lift_splat_bwd_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "stp3_lift_splat_bwd": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I, _F,
                                  _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _V, _V, _V]),
+    "stp3_lift_splat_frames_allgather_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I,
+                                                  _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _I,
+                                                  ctypes.POINTER(ctypes.c_void_p), _V]),
     "stp3_bev_discount": (_I, [_V, _I, _I, _I, _I, _I, _F, _V, _V, _V]),
     "stp3_conv_fwd": (_I, [ctypes.POINTER(ConvDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, ctypes.POINTER(ConvHead), _V]),
     "stp3_lift_splat_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP,

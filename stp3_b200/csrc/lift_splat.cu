@@ -85,8 +85,8 @@ __device__ __forceinline__ void flush_segment(float* gbase, unsigned char* obase
 // fall into one pillar -- every pair of a level camera, about half of them one degree off level.  It runs on the
 // warp-level tensor-core path (mma.sync.m16n8k16, bf16 operands, fp32 accumulate) with both operands split into bf16
 // hi + lo and the three products hi*hi + hi*lo + lo*hi, i.e. ~16 significand bits per operand like the hi/lo planes the
-// BEV grid is stored in downstream.  A pair whose points fall into TWO pillars takes a second pass with the operand
-// masked to the second pillar; anything beyond that is left to a scalar segmented walk.
+// BEV grid is stored in downstream.  A pair whose points fall into several pillars takes one more pass per pillar with
+// the operand masked to it (up to kSegPasses); anything beyond that is left to a scalar segmented walk.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   hi = ptx::pack_bf16x2(x0, x1);
   lo = ptx::pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
@@ -358,6 +358,7 @@ lift_splat_scatter_kernel(const LiftSplatParams p) {
 //            NCHW: 1 box (4 w, Hf, 64 ch)  -> s_feat[64][Hf][4]   (only the mma B-fragment loads of phase C read it: 64 LDS
 //                  per warp and column, so their bank conflicts do not matter)
 constexpr int kTmaTW = 4;
+constexpr int kSegPasses = 4;      // pillars per (depth bin, image column) pair the tensor-core passes cover
 
 // Pillar ranks of the depth bins [da, db) of one pixel's ray, bit-exact with the reference (lift_geom.cuh).  NC ego-motion
 // links (0, 1, 2) are compile-time and live in registers with the camera transform; NC = 3: two in registers, the rest of a
@@ -408,9 +409,8 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   float* s_feat = s_stage + ((D * npix + 31) & ~31);               // feature tile (TMA destination)
   float* s_prob = s_feat + ((feat_floats + 31) & ~31);             // [D][TW][HP]
   int* s_rank = reinterpret_cast<int*>(s_prob + D * TW * HP);      // [D][TW][HP]
-  int* s_seg0 = s_rank + D * TW * HP;                              // [D][TW] first pillar of the (depth, column) pair, -1 = none
-  int* s_seg1 = s_seg0 + D * TW;                                   // [D][TW] second pillar, -1 = none
-  int* s_nseg = s_seg1 + D * TW;                                   // [D][TW] distinct pillars: 0, 1, 2, 3 (= three or more)
+  int* s_seg = s_rank + D * TW * HP;                               // [kSegPasses][D][TW] k-th distinct pillar of the (depth, column) pair, -1 = none
+  int* s_nseg = s_seg + kSegPasses * D * TW;                       // [D][TW] distinct pillars: 0 .. kSegPasses, kSegPasses + 1 = more
   int* s_cinfo = s_nseg + D * TW;                                  // [TW] max of s_nseg over the column's depth bins
   float* s_mat = reinterpret_cast<float*>(s_cinfo + TW);           // camera 12 + (kMaxFrames-1) * 12 pose floats
   float* s_ys = s_mat + 12 * kMaxFrames;
@@ -550,17 +550,26 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
   __syncthreads();
   if (tid < TW) s_cinfo[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < D * TW; i += nthr) {       // summary of every (depth, column) pair: its first two pillars
+  for (int i = tid; i < D * TW; i += nthr) {       // summary of every (depth, column) pair: its first kSegPasses pillars
     const int* r = s_rank + i * HP;
-    int r0 = -1, r1 = -1, n = 0;
+    int rs[kSegPasses];
+#pragma unroll
+    for (int k = 0; k < kSegPasses; ++k) rs[k] = -1;
+    int n = 0;
     for (int h = 0; h < Hf; ++h) {
       const int v = r[h];
-      if (v >= 0 && v != r0 && v != r1) {
-        if (n == 0) r0 = v; else if (n == 1) r1 = v;
-        n = min(n + 1, 3);
+      bool seen = v < 0;                           // masked rows carry probability 0: they never split a pair
+#pragma unroll
+      for (int k = 0; k < kSegPasses; ++k) seen |= (v == rs[k]);
+      if (!seen) {
+#pragma unroll
+        for (int k = 0; k < kSegPasses; ++k) if (k == n) rs[k] = v;
+        n = min(n + 1, kSegPasses + 1);
       }
     }
-    s_seg0[i] = r0; s_seg1[i] = r1; s_nseg[i] = n;  // masked rows carry probability 0: they never split a pair
+#pragma unroll
+    for (int k = 0; k < kSegPasses; ++k) s_seg[k * D * TW + i] = rs[k];
+    s_nseg[i] = n;
     if (n > 0) atomicMax(&s_cinfo[i % TW], n);
   }
   __syncthreads();
@@ -606,9 +615,9 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
           }
         }
       }
-      const int n_pass = min(cmax, 2);
+      const int n_pass = min(cmax, kSegPasses);
       for (int pass = 0; pass < n_pass; ++pass) {
-        const int* seg = pass == 0 ? s_seg0 : s_seg1;
+        const int* seg = s_seg + pass * D * TW;
         for (int mt = 0; mt < n_mt; ++mt) {
           const int d_lo = mt * 16 + g, d_hi = d_lo + 8;
           const int seg_lo = d_lo < D ? seg[d_lo * TW + wl] : -1;
@@ -653,21 +662,26 @@ lift_splat_scatter_tma_kernel(const __grid_constant__ LiftSplatTmaMaps maps, con
           }
         }
       }
-      // leftovers: (depth, column) pairs that touch three or more pillars -- segmented walk over the rows that belong
-      // to neither of the two pillars the tensor-core passes covered; lanes own channel pairs, the two warps of the
+      // leftovers: (depth, column) pairs that touch more than kSegPasses pillars -- segmented walk over the rows that
+      // belong to none of the pillars the tensor-core passes covered; lanes own channel pairs, the two warps of the
       // column split the depth bins
-      if (cmax >= 3) {
+      if (cmax > kSegPasses) {
         const int c = c0 + 2 * lane;
         for (int d = nhalf; d < D; d += 2) {
-          if (s_nseg[d * TW + wl] < 3) continue;
-          const int e0 = s_seg0[d * TW + wl], e1 = s_seg1[d * TW + wl];
+          if (s_nseg[d * TW + wl] <= kSegPasses) continue;
+          int ex[kSegPasses];
+#pragma unroll
+          for (int k = 0; k < kSegPasses; ++k) ex[k] = s_seg[k * D * TW + d * TW + wl];
           const int* rk = s_rank + (d * TW + wl) * HP;
           const float* pr = s_prob + (d * TW + wl) * HP;
           int cur = -1;
           float a0 = 0.f, a1 = 0.f;
           for (int h = 0; h < Hf; ++h) {
             const int r = rk[h];
-            if (r < 0 || r == e0 || r == e1) continue;      // warp-uniform
+            bool skip = r < 0;
+#pragma unroll
+            for (int k = 0; k < kSegPasses; ++k) skip |= (r == ex[k]);
+            if (skip) continue;                             // warp-uniform
             if (r != cur) {
               if (cur >= 0) flush_segment(gbase, obase, cur, C, c, true, lane == 0 && c0 == 0, a0, a1);
               cur = r; a0 = 0.f; a1 = 0.f;
@@ -815,10 +829,22 @@ bev_finalize_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, f
 // (LDG.256 / STG.256) and the lanes of a pillar touch one contiguous row -- the lane-per-pillar mapping of the kernel
 // above would write half sectors 128 bytes apart here.  Same arithmetic, same workspace-cleaning contract; the CTA
 // clears the occupancy bytes itself because it covers all channels of its pillars.
-template <int LPP, int SMAX>
+// PeerOut (frame-sharded mode, fused with the all-gather): instead of one local tensor the fp32 channels-last rows of
+// frame bt go to EVERY rank's gathered (n_frames, nvox, C) buffer, slot first_slot + bt -- plain st.global on
+// peer-mapped addresses (NVLink 5 / NVSwitch), so the collective is the kernel's own epilogue and no separate
+// all-gather launch follows.
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+  float* ptr[kMaxPeers];
+  int n;             // 0: not used (write `out`)
+  int first_slot;
+};
+
+template <int LPP, int SMAX, bool PEERS>
 __global__ void __launch_bounds__(256)
 bev_finalize_cl_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ, float* __restrict__ out,
-                       float* __restrict__ pool_sum, int S, int nvox, float discount, int out_layout) {
+                       float* __restrict__ pool_sum, int S, int nvox, float discount, int out_layout,
+                       const __grid_constant__ PeerOut peers) {
   constexpr int C = LPP * 16, PPB = 256 / LPP;
   __shared__ float s_pool[8][SMAX][C];
   const int b = blockIdx.y;
@@ -869,12 +895,23 @@ bev_finalize_cl_kernel(float* __restrict__ grid, unsigned char* __restrict__ occ
           ptx::st_global_v8(hp, hw);
           ptx::st_global_v8(lp, lw);
         } else {
-          float* dst = out + (bt * nvox + pcell) * C + c0;
           uint32_t w0[8], w1[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(acc[i]); w1[i] = __float_as_uint(acc[8 + i]); }
-          ptx::st_global_v8(dst, w0);
-          ptx::st_global_v8(dst + 8, w1);
+          if constexpr (!PEERS) {
+            float* dst = out + (bt * nvox + pcell) * C + c0;
+            ptx::st_global_v8(dst, w0);
+            ptx::st_global_v8(dst + 8, w1);
+          } else {
+            const size_t off = ((size_t)(peers.first_slot + bt) * nvox + pcell) * C + c0;
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q) {          // the all-gather: one row to every rank's buffer
+              if (q < peers.n) {
+                ptx::st_global_v8(peers.ptr[q] + off, w0);
+                ptx::st_global_v8(peers.ptr[q] + off + 8, w1);
+              }
+            }
+          }
         }
       }
       if (pool_sum) {
@@ -1027,12 +1064,17 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
                            int use_depth_distribution,
                            int32_t* ranks_out, float* pool_sum,
                            void* workspace, size_t workspace_bytes,
-                           float* out, int out_layout, int f_begin, int f_count, void* stream_) {
+                           float* out, int out_layout, int f_begin, int f_count, void* stream_,
+                           const PeerOut* peers = nullptr) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const bool raw = f_count >= 0;
+  PeerOut po;
+  po.n = 0; po.first_slot = 0;
+  for (int i = 0; i < kMaxPeers; ++i) po.ptr[i] = nullptr;
+  if (peers) po = *peers;
   if (raw) STP3_CHECK_ARG(f_begin >= 0 && f_count > 0 && f_begin + f_count <= B * S, "frame range outside [0, B*S)");
   const int Bw = raw ? f_count : B, Sw = raw ? 1 : S;      // shape of the scatter grid / finalize launch
-  STP3_CHECK_ARG(feat && cam_M && cam_t && ego_R && ego_t && xs && ys && ds && bev_off && bev_res && out && workspace,
+  STP3_CHECK_ARG(feat && cam_M && cam_t && ego_R && ego_t && xs && ys && ds && bev_off && bev_res && (out || po.n > 0) && workspace,
                  "stp3_lift_splat_fwd: null pointer argument");
   STP3_CHECK_ARG(use_depth_distribution == 0 || depth_logits, "depth_logits is NULL but use_depth_distribution=1");
   STP3_CHECK_ARG(B > 0 && S > 0 && N > 0 && D > 0 && Hf > 0 && Wf > 0 && C > 0, "non-positive dimension");
@@ -1132,7 +1174,7 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
         const int HP = (Hf + 3) & ~3, npix = Hf * 4;
         const int feat_floats = npix * kCChunk;
         const size_t smem_tma = 128 + ((size_t)((D * npix + 31) & ~31) + ((feat_floats + 31) & ~31) + 2 * (size_t)D * 4 * HP +
-                                       3 * (size_t)D * 4 + 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
+                                       (kSegPasses + 1) * (size_t)D * 4 + 4 + 12 * kMaxFrames + Hf + D + kScatterThreads + 2) * 4 + 16;
         if (smem_tma <= 113 * 1024) {
           STP3_CUDA_OK(cudaFuncSetAttribute(lift_splat_scatter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem_tma));
@@ -1159,10 +1201,17 @@ static int lift_splat_impl(const float* feat, int feat_layout, const float* dept
     const int ppb = 256 / (C / 16);
     pool_blocks = ceil_div(nvox, ppb);
     dim3 cgrid(pool_blocks, Bw);
-    if (C == 32) bev_finalize_cl_kernel<2, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
-    else if (C == 64) bev_finalize_cl_kernel<4, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
-    else bev_finalize_cl_kernel<8, 4><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout);
+#define STP3_FIN_CL(LPP_, PEERS_) \
+    bev_finalize_cl_kernel<LPP_, 4, PEERS_><<<cgrid, 256, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, nvox, discount, out_layout, po)
+    if (po.n > 0) {
+      STP3_CHECK_ARG(out_layout == 1, "peer outputs are fp32 channels-last");
+      if (C == 32) STP3_FIN_CL(2, true); else if (C == 64) STP3_FIN_CL(4, true); else STP3_FIN_CL(8, true);
+    } else {
+      if (C == 32) STP3_FIN_CL(2, false); else if (C == 64) STP3_FIN_CL(4, false); else STP3_FIN_CL(8, false);
+    }
+#undef STP3_FIN_CL
   } else {
+    STP3_CHECK_ARG(po.n == 0, "peer outputs need C in {32, 64, 128} (channels-last finalize kernel)");
 #define STP3_FINALIZE(VEC, SMAX) \
   bev_finalize_kernel<VEC, SMAX><<<fgrid, fblock, 0, stream>>>(p.grid, p.occ, out, pool_part, Sw, C, nvox, discount, out_layout)
   if (C % 8 == 0) { if (Sw <= 4) STP3_FINALIZE(true, 4); else STP3_FINALIZE(true, 8); }
@@ -1211,6 +1260,27 @@ extern "C" int stp3_lift_splat_frames_fwd(const float* feat, int feat_layout, co
   return lift_splat_impl(feat, feat_layout, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, nx, ny,
                          nz, 0.f, B, S, N, D, Hf, Wf, C, use_depth_distribution, nullptr, nullptr, workspace,
                          workspace_bytes, out_raw, 1, f_begin, f_count, stream);
+}
+
+extern "C" int stp3_lift_splat_frames_allgather_fwd(const float* feat, int feat_layout, const float* depth_logits,
+                                                    const float* cam_M, const float* cam_t, const float* ego_R, const float* ego_t,
+                                                    const float* xs, const float* ys, const float* ds,
+                                                    const float* bev_off, const float* bev_res,
+                                                    int nx, int ny, int nz,
+                                                    int B, int S, int N, int D, int Hf, int Wf, int C,
+                                                    int use_depth_distribution, int f_begin, int f_count,
+                                                    void* workspace, size_t workspace_bytes,
+                                                    int n_peers, void* const* peer_out, void* stream) {
+  STP3_CHECK_ARG(f_count > 0, "stp3_lift_splat_frames_allgather_fwd: empty frame range");
+  STP3_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers && peer_out, "n_peers must be in [1, %d]", kMaxPeers);
+  PeerOut po;
+  po.n = n_peers; po.first_slot = f_begin;
+  for (int i = 0; i < kMaxPeers; ++i) po.ptr[i] = i < n_peers ? static_cast<float*>(peer_out[i]) : nullptr;
+  for (int i = 0; i < n_peers; ++i)
+    STP3_CHECK_ARG(po.ptr[i] && (reinterpret_cast<uintptr_t>(po.ptr[i]) & 31) == 0, "peer buffer %d is null or not 32-byte aligned", i);
+  return lift_splat_impl(feat, feat_layout, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, nx, ny,
+                         nz, 0.f, B, S, N, D, Hf, Wf, C, use_depth_distribution, nullptr, nullptr, workspace,
+                         workspace_bytes, nullptr, 1, f_begin, f_count, stream, &po);
 }
 
 namespace stp3 {

@@ -195,11 +195,14 @@ class STP3(nn.Module):
         self._mark("decoder")
         return output
 
-    def forward_features_frame_sharded(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion):
+    def forward_features_frame_sharded(self, feat, depth_logits, intrinsics, extrinsics, future_egomotion, gather="nccl"):
         """Latency mode for a global batch smaller than the number of GPUs: the B*S camera frames are
         split across the ranks of the default process group, every rank splats only its frames, ONE all-gather of
         the raw BEV grids follows, and the (cheap, elementwise) discount recurrence, the temporal model and the
-        decoder run replicated.  Every rank passes the same full inputs and returns the same outputs."""
+        decoder run replicated.  Every rank passes the same full inputs and returns the same outputs.
+        gather = "nccl": ncclAllGather of the frames; gather = "peer": the finalize kernel's epilogue stores every frame
+        into all ranks' buffers over NVLink itself (symmetric memory, parallel.PeerFrameBuffer) -- compute and collective in
+        one kernel, bracketed by two device-side barriers."""
         from .. import parallel
         S = self.receptive_field
         dev = feat.device
@@ -212,14 +215,30 @@ class STP3(nn.Module):
         off, res, dim = self._bev_host()
         rank, world = parallel.world()
         f0, fc = parallel.shard_batch(B * S, rank, world)
-        if fc > 0:
-            raw = ops.lift_splat_frames(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(),
-                                        off, res, dim, f0, fc,
-                                        use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
-                                        workspace=self._ws)
+        if gather == "peer" and world > 1:
+            key = (B * S, X, Y, C, str(dev))
+            pf = self.__dict__.get("_peer_frames")
+            if pf is None or pf[0] != key:
+                pf = (key, parallel.PeerFrameBuffer(B * S, X, Y, C, dev))
+                self.__dict__["_peer_frames"] = pf
+            pf = pf[1]
+            pf.barrier()                       # every rank has consumed the buffer's previous contents
+            if fc > 0:
+                ops.lift_splat_frames(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(),
+                                      off, res, dim, f0, fc,
+                                      use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
+                                      workspace=self._ws, peer_ptrs=pf.ptrs)
+            pf.barrier()                       # every rank's stores have landed
+            raw = pf.buf.view(B, S, X, Y, C)
         else:
-            raw = torch.empty((0, X, Y, C), dtype=torch.float32, device=dev)
-        raw = parallel.all_gather_frames(raw, B * S).view(B, S, X, Y, C)
+            if fc > 0:
+                raw = ops.lift_splat_frames(feat, depth_logits, h["cam_M"], h["cam_t"], h["ego_R"], h["ego_t"], *self._axes(),
+                                            off, res, dim, f0, fc,
+                                            use_depth_distribution=self.cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION,
+                                            workspace=self._ws)
+            else:
+                raw = torch.empty((0, X, Y, C), dtype=torch.float32, device=dev)
+            raw = parallel.all_gather_frames(raw, B * S).view(B, S, X, Y, C)
         planes = ops.bev_discount(raw, float(self.discount))
         x = dense.HL(planes[0], planes[1], C)
         output = {'depth_prediction': depth_logits, 'cam_front': None}

@@ -175,9 +175,12 @@ def lift_splat_autograd(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, 
 
 def lift_splat_frames(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds, bev_off, bev_res, bev_dim,
                       f_begin: int, f_count: int, *, feat_channels_last: bool = False,
-                      use_depth_distribution: bool = True, workspace: Optional[Workspace] = None) -> torch.Tensor:
+                      use_depth_distribution: bool = True, workspace: Optional[Workspace] = None,
+                      peer_ptrs=None) -> Optional[torch.Tensor]:
     """Frame-sharded lift-splat: RAW (no discount recurrence) channels-last splats (f_count, X, Y, C) fp32 of the flat
-    frames f_begin + [0, f_count), f = b*S + t.  See stp3_lift_splat_frames_fwd in include/stp3_b200.h."""
+    frames f_begin + [0, f_count), f = b*S + t.  See stp3_lift_splat_frames_fwd in include/stp3_b200.h.
+    peer_ptrs (list of device pointers, one (B*S, X, Y, C) fp32 buffer per rank): the finalize epilogue stores the frames
+    into slot f of every rank's buffer instead (stp3_lift_splat_frames_allgather_fwd); returns None."""
     _require_cuda(feat, depth_logits)
     dev = feat.device
     if feat_channels_last:
@@ -193,6 +196,19 @@ def lift_splat_frames(feat, depth_logits, cam_M, cam_t, ego_R, ego_t, xs, ys, ds
     L = _lib.lib()
     need = L.stp3_lift_splat_workspace_bytes(f_count, 1, C, nx, ny)
     ws = (workspace or _default_ws).get(need, dev)
+    if peer_ptrs is not None:
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+        with torch.cuda.device(dev):
+            code = L.stp3_lift_splat_frames_allgather_fwd(
+                feat.data_ptr(), int(feat_channels_last), depth_logits.data_ptr() if depth_logits is not None else None,
+                cam_M.data_ptr(), cam_t.data_ptr(), ego_R.data_ptr(), ego_t.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+                ds.data_ptr(), _host3(bev_off), _host3(bev_res), nx, ny, nz, B, S, N, D, Hf, Wf, C,
+                int(use_depth_distribution), int(f_begin), int(f_count), ws.data_ptr(), ws.numel(), len(peer_ptrs), arr,
+                torch.cuda.current_stream(dev).cuda_stream)
+        if code != 0:
+            (workspace or _default_ws).reset()
+        _lib.check(code, "stp3_lift_splat_frames_allgather_fwd")
+        return None
     out = torch.empty((f_count, nx, ny, C), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         code = L.stp3_lift_splat_frames_fwd(

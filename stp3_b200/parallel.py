@@ -77,3 +77,20 @@ def all_gather_frames(local: torch.Tensor, n_frames: int) -> torch.Tensor:
     if all(c == cmax for c in counts):
         return gathered
     return torch.cat([gathered[r * cmax:r * cmax + c] for r, c in enumerate(counts)])
+
+
+class PeerFrameBuffer:
+    """Every rank's (n_frames, X, Y, C) fp32 gather buffer in symmetric memory (torch.distributed._symmetric_memory: CUDA
+    peer mappings over NVLink), so that the frame-sharded lift-splat can store its frames into all ranks' buffers from
+    its own epilogue (stp3_lift_splat_frames_allgather_fwd) instead of running a separate all-gather.
+    barrier() = device-side cross-rank barrier on the current stream (signal pads of the symmetric allocation)."""
+
+    def __init__(self, n_frames: int, X: int, Y: int, C: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty((n_frames, X, Y, C), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def barrier(self):
+        self.hdl.barrier()
