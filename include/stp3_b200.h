@@ -193,6 +193,30 @@ int stp3_conv_fwd(const stp3_conv_desc* desc, const void* x_hi, const void* x_lo
                   float* y_f32, const stp3_conv_head* head /* may be NULL */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * ASPP branches + projection of a DeepLabHead as ONE back-to-back tensor-core kernel (stp3/layers/convolutions.py:242-270):
+ *   y = relu(BN(project.0(cat_b relu(BN(conv_b(x))))))   for the spatial branches b (1x1 and the dilated 3x3s); the
+ * global-pool branch is spatially constant and enters through img_bias like in stp3_conv_fwd.  The 4 x 128-channel concat
+ * tensor never exists: every branch's activated 16x16x128 tile is converted to bf16 hi/lo planes in shared memory and
+ * multiplied with its slice of the projection weights while the next branch's convolution runs.  hidden = 128 channels.
+ *   x_hi, x_lo  (B, T, H, W, in_cstride) bf16 planes, channels [0, cin) read
+ *   w           bf16 rows of 64 (K-major), blocks of [hi: 128 rows][lo: 128 rows]:
+ *               first one block per (tap of branch 0.., K block of cin) -- BN folded, rows = hidden channels --
+ *               then two per branch for the projection (rows = output channels, K = the branch's hidden channels 0..63, 64..127)
+ *   br_bias     [n_br][128] fp32 folded BN shifts of the branches;  img_bias [B*T][128] fp32 projection bias table
+ *   y_hi, y_lo  (B*T, H, W, out_cstride) bf16 planes, channels [out_coff, out_coff + 128) written
+ */
+typedef struct stp3_aspp_desc {
+  int B, T, H, W;
+  int in_cstride, cin;
+  int n_br;                   /* 1 .. 4 spatial branches */
+  int n_taps[4];              /* 1 .. 9 each; every branch must contain its centre tap (0, 0) */
+  signed char taps[4][9][2];  /* (dy, dx) input offsets */
+  int out_cstride, out_coff;
+} stp3_aspp_desc;
+int stp3_aspp_fused_fwd(const stp3_aspp_desc* desc, const void* x_hi, const void* x_lo, const void* w,
+                        const float* br_bias, const float* img_bias, void* y_hi, void* y_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Memory-bound helpers of the dense path (all tensors channels-last bf16 hi/lo planes unless noted).
  */
 /* fp32 (n_img,C,H,W) [channels_last=0, the reference's NCHW] or (n_img,H,W,C) [1] -> hi/lo (n_img,H,W,cp), padding 0.

@@ -30,6 +30,12 @@ class ConvDesc(ctypes.Structure):
                 ("k_lo", _I), ("k_hi", _I), ("f32_layout", _I)]
 
 
+class AsppDesc(ctypes.Structure):
+    """Mirror of stp3_aspp_desc (include/stp3_b200.h)."""
+    _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("in_cstride", _I), ("cin", _I), ("n_br", _I),
+                ("n_taps", _I * 4), ("taps", ((ctypes.c_byte * 2) * 9) * 4), ("out_cstride", _I), ("out_coff", _I)]
+
+
 class ConvHead(ctypes.Structure):
     """Mirror of stp3_conv_head (include/stp3_b200.h)."""
     _fields_ = [("n_out", _I), ("w", _V), ("b", _V), ("out", _V * 8), ("img_stride", ctypes.c_longlong * 8),
@@ -51,6 +57,7 @@ SIGNATURES = {
     "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _V]),
     "stp3_lift_splat_frames_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I,
                                         _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _V, _V]),
+    "stp3_aspp_fused_fwd": (_I, [ctypes.POINTER(AsppDesc), _V, _V, _V, _V, _V, _V, _V, _V]),
     "stp3_lift_splat_bwd_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "stp3_lift_splat_bwd": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I, _F,
                                  _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _V, _V, _V]),

@@ -1,0 +1,433 @@
+// ASPP branches + 1x1 projection as ONE back-to-back tcgen05 kernel (DeepLabHead of the temporal model,
+// stp3/layers/convolutions.py:242-270: four conv/BN/ReLU branches of the same input, concatenated, then project.0).
+//
+// The unfused form writes the 4 x 128-channel concat tensor to HBM (4 x 246 MB for a 4-sample step) and reads it back
+// (984 MB) -- the largest avoidable traffic of the dense path.  Here a CTA pair keeps a 16x16-pixel tile on chip:
+//
+//   for every branch b:   acc1  = sum_taps A(x, tap) . W_b[tap]            (tcgen05.mma cta_group::2, M = 256, N = 128)
+//                         P     = hi/lo split of relu(acc1 + bias_b)       (epilogue warps: TMEM -> registers -> SHARED memory,
+//                                                                           written in the 128B-swizzled K-major operand layout)
+//                         acc2 += P . W_proj[:, b-th 128 input channels]   (second MMA chain, A operand = P)
+//   out = hi/lo split of relu(acc2 + per-image bias)                       (the global-pool branch is that bias)
+//
+// Same precision scheme as conv_tcgen05.cu (bf16 hi/lo planes, hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), so the
+// result matches the unfused path to the last few bits of the split.
+//
+//   warps : 0 = TMA producer (activation ring + weight ring, both CTAs), 1 = MMA issuer (leader CTA), 2..9 = epilogue
+//   MMA order per tile: main(0), main(1), proj(0), main(2), proj(1), main(3), proj(2), proj(3) -- the projection of branch
+//   b is issued after the main loop of branch b+1, so the tensor pipe works on b+1 while the epilogue converts b
+//   TMEM  : acc1 double-buffered (2 x 128 columns), acc2 128 columns
+//   smem  : 3 activation stages (32 KB) + 3 weight stages (16 KB) + P (2 K-blocks x hi/lo x 16 KB = 64 KB) = 208 KB
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace stp3 {
+
+constexpr int kAsppThreads = 320;                 // 2 + 8 warps
+constexpr int kAsppMaxBranches = 4;
+constexpr int kAsppMaxTaps = 9 * kAsppMaxBranches;
+constexpr int kAsppNA = 3, kAsppNB = 3;
+constexpr int kAStage = 2 * 8 * 16 * 128;         // hi + lo planes of 8 image rows x 16 pixels x 64 channels
+constexpr int kBStage = 2 * 64 * 128;             // hi + lo rows of this CTA's half (64) of the 128 weight rows
+constexpr int kPPlane = 128 * 128;                // 128 pixel rows x 64 bf16
+constexpr int kAsppHidden = 128;
+
+struct AsppParams {
+  int n_img, T, T_total, H, W;
+  int tiles_x, tiles_y, n_tiles;
+  int kblocks;
+  int n_br;
+  int br_tap0[kAsppMaxBranches + 1];
+  signed char tap[kAsppMaxTaps][2];               // (dy, dx)
+  const float* br_bias;                           // [n_br][128]
+  const float* img_bias;                          // [n_img][128]
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int out_cstride, out_coff;
+};
+
+__device__ __forceinline__ bool aspp_tap_is_padding(const AsppParams& p, int t, int oy_tile, int ox0) {
+  const int ylo = oy_tile + p.tap[t][0], yhi = oy_tile + 15 + p.tap[t][0];
+  const int xlo = ox0 + p.tap[t][1], xhi = ox0 + 15 + p.tap[t][1];
+  return yhi < 0 || ylo >= p.H || xhi < 0 || xlo >= p.W;
+}
+
+__global__ void __launch_bounds__(kAsppThreads, 1)
+aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_w, const AsppParams p) {
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cta = (int)(blockIdx.x >> 1), n_cta = (int)(gridDim.x >> 1);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = a_ring + kAsppNA * kAStage;
+  unsigned char* p_buf = b_ring + kAsppNB * kBStage;            // [kb2][hi | lo][128 rows x 128 B]
+  float* s_bias = reinterpret_cast<float*>(p_buf + 4 * kPPlane);   // [n_br][128]
+  float* s_wb = s_bias + kAsppMaxBranches * kAsppHidden;           // [8 warps][64] per-image bias slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + 8 * 64);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kAsppNA;
+  uint64_t* b_full = a_empty + kAsppNA;
+  uint64_t* b_empty = b_full + kAsppNB;
+  uint64_t* acc1_full = b_empty + kAsppNB;        // [2]
+  uint64_t* acc1_empty = acc1_full + 2;           // [2]
+  uint64_t* p_full = acc1_empty + 2;              // [2] (per K block of P)
+  uint64_t* p_empty = p_full + 2;                 // [2]
+  uint64_t* acc2_full = p_empty + 2;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::griddep_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
+    for (int i = 0; i < kAsppNA; ++i) { ptx::mbar_init(&a_full[i], 2); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kAsppNB; ++i) { ptx::mbar_init(&b_full[i], 2); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc1_full[i], 1);
+      ptx::mbar_init(&acc1_empty[i], 16);         // 8 epilogue warps of both CTAs
+      ptx::mbar_init(&p_full[i], 8);              // the 4 warps of one column half, both CTAs
+      ptx::mbar_init(&p_empty[i], 1);
+    }
+    ptx::mbar_init(acc2_full, 1);
+    ptx::mbar_init(acc2_empty, 16);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_slot);
+  for (int i = threadIdx.x; i < p.n_br * kAsppHidden; i += blockDim.x) s_bias[i] = p.br_bias[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int proj_blk0 = p.br_tap0[p.n_br] * p.kblocks;          // first projection block of the weight tensor
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    ptx::griddep_wait();
+    int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+    auto load_b = [&](int blk) {                   // weight block `blk`: [hi 128 rows][lo 128 rows]; this CTA takes 64 of each
+      ptx::mbar_wait(&b_empty[bs], bph ^ 1);
+      if (ptx::elect_one_sync()) {
+        const uint32_t bar = ptx::mapa(ptx::smem_u32(&b_full[bs]), 0);
+        unsigned char* dst = b_ring + (size_t)bs * kBStage;
+        ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)kBStage);
+        ptx::tma_load_2d_pair(dst, &tm_w, bar, 0, blk * 256 + (int)rank * 64);
+        ptx::tma_load_2d_pair(dst + 64 * 128, &tm_w, bar, 0, blk * 256 + 128 + (int)rank * 64);
+      }
+      __syncwarp();
+      if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
+    };
+    for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+      const int oy_tile = (rem / p.tiles_x) * 16, ox0 = (rem % p.tiles_x) * 16;
+      const int oy0 = oy_tile + (int)rank * 8;
+      const int bidx = img / p.T, tidx = img % p.T;
+      for (int s = 0; s <= p.n_br; ++s) {
+        if (s < p.n_br) {
+          for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
+            if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              ptx::mbar_wait(&a_empty[as], aph ^ 1);
+              if (ptx::elect_one_sync()) {
+                unsigned char* sa = a_ring + (size_t)as * kAStage;
+                const uint32_t bar = ptx::mapa(ptx::smem_u32(&a_full[as]), 0);
+                ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)kAStage);
+                ptx::tma_load_5d_pair(sa, &tm_a_hi, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
+                ptx::tma_load_5d_pair(sa + kAStage / 2, &tm_a_lo, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
+              }
+              __syncwarp();
+              if (++as == kAsppNA) { as = 0; aph ^= 1; }
+              load_b(t * p.kblocks + kb);
+            }
+          }
+        }
+        if (s >= 1) { load_b(proj_blk0 + (s - 1) * 2); load_b(proj_blk0 + (s - 1) * 2 + 1); }   // projection weights of branch s-1
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader) =====================
+    const uint32_t idesc = ptx::umma_idesc_bf16(256, kAsppHidden);
+    int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+    int buf1 = 0; uint32_t acc1_ph = 0, pph = 0, t2ph = 0;
+    auto issue = [&](uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t accumulate) {
+      const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_lo);
+      const uint64_t db_hi = ptx::umma_desc_k_sw128(b_hi), db_lo = ptx::umma_desc_k_sw128(b_lo);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t koff = (uint64_t)((k * 32) >> 4);
+        ptx::umma_bf16_pair(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate | (uint32_t)k);
+        ptx::umma_bf16_pair(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+        ptx::umma_bf16_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
+      }
+    };
+    for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+      const int rem = tile % tiles_per_img;
+      const int oy_tile = (rem / p.tiles_x) * 16, ox0 = (rem % p.tiles_x) * 16;
+      for (int s = 0; s <= p.n_br; ++s) {
+        if (s < p.n_br) {
+          // ---- main(s): acc1[buf1] = sum over the branch's taps
+          ptx::mbar_wait(&acc1_empty[buf1], acc1_ph ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf1 * kAsppHidden);
+          uint32_t accumulate = 0;
+          for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
+            if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              ptx::mbar_wait(&a_full[as], aph);
+              ptx::mbar_wait(&b_full[bs], bph);
+              ptx::tc_fence_after();
+              if (ptx::elect_one_sync()) {
+                const uint32_t a_hi = ptx::smem_u32(a_ring + (size_t)as * kAStage);
+                const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBStage);
+                issue(tmem_d, a_hi, a_hi + kAStage / 2, b_hi, b_hi + 64 * 128, accumulate);
+                ptx::umma_commit_pair(&b_empty[bs]);
+                ptx::umma_commit_pair(&a_empty[as]);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++as == kAsppNA) { as = 0; aph ^= 1; }
+              if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
+            }
+          }
+          if (ptx::elect_one_sync()) ptx::umma_commit_pair(&acc1_full[buf1]);
+          __syncwarp();
+          if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
+        }
+        if (s >= 1) {
+          // ---- proj(s-1): acc2 += P . W_proj[:, branch s-1]
+          const int j = s - 1;
+          if (j == 0) {                            // the previous tile's output has left acc2
+            ptx::mbar_wait(acc2_empty, t2ph ^ 1);
+            ptx::tc_fence_after();
+          }
+          const uint32_t tmem_d2 = tmem_base + 2u * kAsppHidden;
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            ptx::mbar_wait(&p_full[kb2], pph);
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one_sync()) {
+              const uint32_t a_hi = ptx::smem_u32(p_buf + (size_t)kb2 * 2 * kPPlane);
+              const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBStage);
+              issue(tmem_d2, a_hi, a_hi + kPPlane, b_hi, b_hi + 64 * 128, (j > 0 || kb2 > 0) ? 1u : 0u);
+              ptx::umma_commit_pair(&b_empty[bs]);
+              ptx::umma_commit_pair(&p_empty[kb2]);
+            }
+            __syncwarp();
+            if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
+          }
+          pph ^= 1;
+          if (j == p.n_br - 1) {
+            if (ptx::elect_one_sync()) ptx::umma_commit_pair(acc2_full);
+            __syncwarp();
+            t2ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue =====================
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;                       // column half = K block of P this warp produces
+    const int r = q * 32 + lane;                   // accumulator row = pixel of this CTA's 8x16 sub-tile
+    const int col0 = half * 64;
+    int buf1 = 0; uint32_t acc1_ph = 0, pph = 0, t2ph = 0;
+    unsigned char* p_hi = p_buf + (size_t)half * 2 * kPPlane + (size_t)r * 128;
+    unsigned char* p_lo = p_hi + kPPlane;
+    const uint32_t sw = (uint32_t)(r & 7);
+    ptx::griddep_wait();
+    for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+      const int oy = (rem / p.tiles_x) * 16 + (int)rank * 8 + (r >> 4), ox = (rem % p.tiles_x) * 16 + (r & 15);
+      {                                            // this warp's slice of the per-image projection bias
+        const float* ib = p.img_bias + (size_t)img * kAsppHidden + col0;
+        float* wb = s_wb + e * 64;
+        __syncwarp();
+        wb[lane] = __ldg(ib + lane); wb[lane + 32] = __ldg(ib + lane + 32);
+        __syncwarp();
+      }
+      for (int b = 0; b < p.n_br; ++b) {
+        ptx::mbar_wait(&acc1_full[buf1], acc1_ph);
+        ptx::mbar_wait(&p_empty[half], pph ^ 1);   // the projection of the previous branch has read P
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf1 * kAsppHidden + col0);
+        const float* bias = s_bias + b * kAsppHidden + col0;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t acc[16];
+          ptx::tmem_ld_32x32b_x16(tmem_acc + j * 16, acc);
+          ptx::tmem_ld_wait();
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = fmaxf(__uint_as_float(acc[2 * i]) + bias[j * 16 + 2 * i], 0.f);
+            const float x1 = fmaxf(__uint_as_float(acc[2 * i + 1]) + bias[j * 16 + 2 * i + 1], 0.f);
+            const uint32_t h = ptx::pack_bf16x2(x0, x1);
+            hw[i] = h;
+            lw[i] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+          }
+          // channels [j*16, j*16+16) of the K block = 16-byte chunks 2j and 2j+1 of the 128-byte row, XOR-swizzled with
+          // the row index (the layout TMA writes and the UMMA descriptor of a SWIZZLE_128B K-major operand expects)
+          const uint32_t c0 = ((uint32_t)(2 * j) ^ sw) << 4, c1 = ((uint32_t)(2 * j + 1) ^ sw) << 4;
+          *reinterpret_cast<uint4*>(p_hi + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(p_hi + c1) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(p_lo + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *reinterpret_cast<uint4*>(p_lo + c1) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();                  // the generic-proxy stores above are read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc1_empty[buf1]), 0));
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&p_full[half]), 0));
+        }
+        pph ^= 1;
+        if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
+      }
+      // ---- output of the projection: relu(acc2 + per-image bias) -> hi/lo planes
+      ptx::mbar_wait(acc2_full, t2ph);
+      ptx::tc_fence_after();
+      t2ph ^= 1;
+      const bool valid = oy < p.H && ox < p.W;
+      const size_t pix = ((size_t)img * p.H + oy) * p.W + ox;
+      const uint32_t tmem_acc2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * kAsppHidden + col0);
+      const float* wb = s_wb + e * 64;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t acc[16];
+        ptx::tmem_ld_32x32b_x16(tmem_acc2 + j * 16, acc);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = fmaxf(__uint_as_float(acc[2 * i]) + wb[j * 16 + 2 * i], 0.f);
+            const float x1 = fmaxf(__uint_as_float(acc[2 * i + 1]) + wb[j * 16 + 2 * i + 1], 0.f);
+            const uint32_t h = ptx::pack_bf16x2(x0, x1);
+            hw[i] = h;
+            lw[i] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+          }
+          const size_t off = pix * p.out_cstride + p.out_coff + col0 + j * 16;
+          ptx::st_global_v8(p.out_hi + off, hw);
+          ptx::st_global_v8(p.out_lo + off, lw);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc2_empty), 0));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc_pair<512>(tmem_base);
+}
+
+typedef CUresult (*PFN_tmapEncodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiledA aspp_encode_fn() {
+  static PFN_tmapEncodeTiledA fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiledA>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace stp3
+
+using namespace stp3;
+
+extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, const void* x_lo, const void* w,
+                                   const float* br_bias, const float* img_bias, void* y_hi, void* y_lo, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  STP3_CHECK_ARG(d && x_hi && x_lo && w && br_bias && img_bias && y_hi && y_lo, "stp3_aspp_fused_fwd: null pointer argument");
+  STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0, "non-positive dimension");
+  STP3_CHECK_ARG(d->in_cstride % 64 == 0 && d->cin % 64 == 0 && d->cin > 0 && d->cin <= d->in_cstride, "input channels: multiples of 64");
+  STP3_CHECK_ARG(d->n_br >= 1 && d->n_br <= kAsppMaxBranches, "1 .. 4 branches");
+  STP3_CHECK_ARG(d->out_cstride % 16 == 0 && d->out_coff % 16 == 0 && d->out_coff + kAsppHidden <= d->out_cstride &&
+                 (reinterpret_cast<uintptr_t>(y_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(y_lo) & 31) == 0,
+                 "output planes: 128 channels at a 16-channel aligned offset, 32-byte aligned");
+  PFN_tmapEncodeTiledA enc = aspp_encode_fn();
+  if (!enc) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  AsppParams p;
+  p.n_img = d->B * d->T; p.T = d->T; p.T_total = d->T; p.H = d->H; p.W = d->W;
+  p.tiles_x = ceil_div(d->W, 16); p.tiles_y = ceil_div(d->H, 16);
+  const long long nt = (long long)p.n_img * p.tiles_x * p.tiles_y;
+  STP3_CHECK_ARG(nt < (1ll << 31), "grid too large");
+  p.n_tiles = (int)nt;
+  p.kblocks = d->cin / 64; p.n_br = d->n_br;
+  int t = 0;
+  for (int b = 0; b < d->n_br; ++b) {
+    STP3_CHECK_ARG(d->n_taps[b] >= 1 && d->n_taps[b] <= 9, "1 .. 9 taps per branch");
+    p.br_tap0[b] = t;
+    bool centre = false;
+    for (int i = 0; i < d->n_taps[b]; ++i, ++t) {
+      p.tap[t][0] = d->taps[b][i][0]; p.tap[t][1] = d->taps[b][i][1];
+      centre |= d->taps[b][i][0] == 0 && d->taps[b][i][1] == 0;
+    }
+    STP3_CHECK_ARG(centre, "every branch needs its centre tap (padding skips rely on it)");
+  }
+  for (int b = d->n_br; b <= kAsppMaxBranches; ++b) p.br_tap0[b] = t;
+  p.br_bias = br_bias; p.img_bias = img_bias;
+  p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
+  p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)d->in_cstride, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->T, (cuuint64_t)d->B};
+    const cuuint64_t strides[4] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
+                                   (cuuint64_t)d->H * d->W * d->in_cstride * 2, (cuuint64_t)d->T * d->H * d->W * d->in_cstride * 2};
+    const cuuint32_t box[5] = {64, 16, 8, 1, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r1 = enc(&tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_hi), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_lo), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+      return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d %d", (int)r1, (int)r2);
+    const int n_blocks = t * p.kblocks + 2 * d->n_br;
+    const cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * 256};
+    const cuuint64_t ws[1] = {128};
+    const cuuint32_t wb[2] = {64, 64};
+    const cuuint32_t we[2] = {1, 1};
+    CUresult r3 = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), wd, ws, wb, we,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r3 != CUDA_SUCCESS) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r3);
+  }
+  const size_t smem_bytes = 1024 + (size_t)kAsppNA * kAStage + (size_t)kAsppNB * kBStage + 4 * (size_t)kPPlane +
+                            (kAsppMaxBranches * kAsppHidden + 8 * 64) * sizeof(float) + 32 * 8 + 16;
+  STP3_CUDA_OK(cudaFuncSetAttribute(aspp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  int num_sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfg = {};
+  unsigned pairs = (unsigned)(nt < num_sms / 2 ? nt : num_sms / 2);
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kAsppThreads);
+  cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, aspp_fused_kernel, &cfg));
+  if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");
+  if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+  STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, aspp_fused_kernel, tm_hi, tm_lo, tm_w, p));
+  STP3_CUDA_OK(cudaGetLastError());
+  return STP3_OK;
+}

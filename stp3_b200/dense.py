@@ -258,6 +258,69 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
     return out
 
 
+@dataclass
+class PackedAspp:
+    w: torch.Tensor            # bf16 rows of 64: [tap/K blocks ...][projection blocks ...], each [hi 128][lo 128]
+    br_bias: torch.Tensor      # (n_br, 128) fp32
+    proj_bias: torch.Tensor    # (128,) fp32
+    taps: List[List[Tuple[int, int]]]
+    cin_p: int
+
+
+def pack_aspp(branches, proj_w: torch.Tensor, proj_b: torch.Tensor) -> PackedAspp:
+    """branches: [(weight (128, Cin, kh, kw) BN-folded, bias (128), dilation)]; proj_w (128, n_br * 128) BN-folded.
+    Layout of stp3_aspp_fused_fwd (include/stp3_b200.h)."""
+    h = 128
+    cin = branches[0][0].shape[1]
+    cin_p = pad_to(cin)
+    kbs = cin_p // KB
+    dev = proj_w.device
+    blocks, taps_all, biases = [], [], []
+    for w, b, dil in branches:
+        assert w.shape[0] == h and w.shape[1] == cin
+        kh, kw = w.shape[2:]
+        taps = []
+        for iy in range(kh):
+            for ix in range(kw):
+                dy, dx = (iy - (kh - 1) // 2) * dil, (ix - (kw - 1) // 2) * dil
+                taps.append((dy, dx))
+                m = torch.zeros((h, cin_p), dtype=torch.float32, device=dev)
+                m[:, :cin] = w[:, :, iy, ix]
+                for kb in range(kbs):
+                    blocks.append(m[:, kb * KB:(kb + 1) * KB])
+        taps_all.append(taps)
+        biases.append(b)
+    for i in range(len(branches)):
+        for kb2 in range(2):
+            blocks.append(proj_w[:, i * h + kb2 * KB: i * h + (kb2 + 1) * KB])
+    m = torch.stack(blocks).float()                                   # (n_blocks, 128, 64)
+    hi, lo = split_hilo(m)
+    packed = torch.stack([hi, lo], dim=1).contiguous()                # (n_blocks, 2, 128, 64)
+    return PackedAspp(packed, torch.stack(biases).float().contiguous(), proj_b.float().contiguous(), taps_all, cin_p)
+
+
+def aspp_fused(x: HL, pa: PackedAspp, img_bias: torch.Tensor, out: Optional[HL] = None, out_coff: int = 0) -> HL:
+    """y = relu(project(cat_b relu(branch_b(x))) + img_bias): stp3_aspp_fused_fwd."""
+    B, T, H, W, cs = x.hi.shape
+    if out is None:
+        out = HL.empty(B, T, H, W, 128, x.hi.device, cp=128)
+    assert img_bias.shape == (B * T, 128) and img_bias.dtype == torch.float32 and img_bias.is_contiguous()
+    d = _lib.AsppDesc()
+    d.B, d.T, d.H, d.W, d.in_cstride, d.cin = B, T, H, W, cs, pa.cin_p
+    d.n_br = len(pa.taps)
+    for b, taps in enumerate(pa.taps):
+        d.n_taps[b] = len(taps)
+        for i, (dy, dx) in enumerate(taps):
+            d.taps[b][i][0], d.taps[b][i][1] = dy, dx
+    d.out_cstride, d.out_coff = out.hi.shape[-1], out_coff
+    with torch.cuda.device(x.hi.device):
+        code = _lib.lib().stp3_aspp_fused_fwd(ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pa.w.data_ptr(),
+                                              pa.br_bias.data_ptr(), img_bias.data_ptr(), out.hi.data_ptr(),
+                                              out.lo.data_ptr(), torch.cuda.current_stream(x.hi.device).cuda_stream)
+    _lib.check(code, "stp3_aspp_fused_fwd")
+    return out
+
+
 def bias_table(pc: PackedConv, n_img: int) -> torch.Tensor:
     """(n_img, bn) per-image bias initialised with the convolution's own bias; the spatially constant branches are
     accumulated on top (pool_bias / small_linear with accumulate=True)."""

@@ -6,6 +6,7 @@
   ASPP / DeepLabHead : the five ASPP branches write straight into one channels-last concat tensor; the global-pool
                    branch is spatially constant and becomes a per-image bias of the 1x1 projection.
 """
+import os
 from typing import Optional
 
 import torch
@@ -102,6 +103,15 @@ class DeepLabHead(nn.Sequential, PackedModule):
         P["conv3"] = dense.pack_conv(w, b, bn=h)
         P["cls"] = dense.pack_conv(self[4].weight.detach().float(), self[4].bias.detach().float())
         P["nb"] = nb
+        # hidden = 128, dilations that fit signed-byte taps: branches + projection as one back-to-back kernel
+        if h == 128 and nb <= 4 and max(aspp.rates) <= 127 and os.environ.get("STP3_ASPP_FUSED", "0") != "0":
+            br = []
+            w, b = dense.fold_bn(aspp.convs[0][0].weight, aspp.convs[0][1])
+            br.append((w, b, 1))
+            for i, r in enumerate(aspp.rates):
+                w, b = dense.fold_bn(aspp.convs[1 + i][0].weight, aspp.convs[1 + i][1])
+                br.append((w, b, r))
+            P["fused"] = dense.pack_aspp(br, wproj[:, :nb * h].reshape(h, nb * h), bproj)
         return P
 
     def forward_hl(self, x: dense.HL, out: Optional[dense.HL] = None, sums: Optional[torch.Tensor] = None) -> dense.HL:
@@ -112,15 +122,18 @@ class DeepLabHead(nn.Sequential, PackedModule):
         B, T, H, W, _ = x.hi.shape
         h, nb = self.hidden, P["nb"]
         dev = x.hi.device
-        cat = dense.HL.empty(B, T, H, W, nb * h, dev, cp=nb * h)
-        for i in range(nb):
-            dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
         if sums is None:
             sums = dense.spatial_sum(x)
         pbias = torch.empty((B * T, P["proj"].bn), dtype=torch.float32, device=x.hi.device)
         dense.pool_bias(sums, T, self.in_channels, H * W, False, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
                         bias=P["proj"].bias)
-        y = dense.conv(cat, P["proj"], relu=True, img_bias=pbias)       # Dropout(0.5) is the identity in eval mode
+        if "fused" in P and x.hi.shape[-1] == P["fused"].cin_p:
+            y = dense.aspp_fused(x, P["fused"], pbias)                  # the concat tensor is never materialised
+        else:
+            cat = dense.HL.empty(B, T, H, W, nb * h, dev, cp=nb * h)
+            for i in range(nb):
+                dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
+            y = dense.conv(cat, P["proj"], relu=True, img_bias=pbias)   # Dropout(0.5) is the identity in eval mode
         y = dense.conv(y, P["conv3"], relu=True)
         return dense.conv(y, P["cls"], out=out)
 

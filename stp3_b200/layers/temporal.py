@@ -131,6 +131,18 @@ class TemporalBlock(PackedModule):
         P["b"] = dense.pack_conv(wt, bt, cin_p=hp)
         ws, bs = dense.fold_bn(p1[1].conv.weight, p1[1].norm)          # (half, half, 1, 3, 3)
         P["c"] = dense.pack_conv(ws, bs, cin_p=hp, in_layout=[(0, half, m1 % 64)])
+        if shared and o + half <= 64:
+            # both mid paths live in ONE 64-channel block (block 2 of the reference: 32 + 32): the causal (2,3,3) and the
+            # (1,3,3) convolution run as one block-diagonal launch -- every activation tile is fetched once instead of
+            # twice (these layers are bound by the L2 -> SM traffic of their shifted windows, not by the MMAs), the
+            # zero off-diagonal blocks cost tensor work that is free here
+            kt = wt.shape[2]
+            wbc = torch.zeros(o + half, 64, kt, 3, 3, device=wt.device)
+            bbc = torch.zeros(o + half, device=wt.device)
+            wbc[:half, :half] = wt
+            wbc[o:o + half, m1:m1 + half, kt - 1] = ws[:, :, 0]          # the (1,3,3) kernel sees the present frame only
+            bbc[:half], bbc[o:o + half] = bt, bs
+            P["bc"] = dense.pack_conv(wbc, bbc, cin_p=64, bn=64)
         wg, bg = dense.fold_bn(self.aggregation[0].conv.weight, self.aggregation[0].norm)
         wg = flat(wg)
         P["agg"] = dense.pack_conv(wg[:, :3 * half].reshape(cout, 3 * half, 1, 1).contiguous(), bg,
@@ -211,8 +223,11 @@ class TemporalBlock(PackedModule):
             else:
                 dense.conv(x, P["a2"], out=agg, out_coff=2 * o, n_store=tail, relu=True,
                            img_bias=const_bias(P.get("a2_c"), P["a2"]))
-        dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
-        dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
+        if "bc" in P:          # one block-diagonal launch for both mid paths (they share a 64-channel block)
+            dense.conv(mid, P["bc"], cin_off=0, out=agg, out_coff=0, n_store=2 * o, relu=True)
+        else:
+            dense.conv(mid, P["b"], cin_off=0, out=agg, out_coff=0, n_store=o, relu=True)
+            dense.conv(mid, P["c"], cin_off=(m1 // 64) * 64, out=agg, out_coff=o, n_store=o, relu=True)
         pbias = None
         if self.use_pyramid_pooling:
             ph, pw = self.pyramid_pooling.pool_sizes[0][1:]

@@ -212,3 +212,24 @@ def test_encoder_forward_vs_reference_golden():
         # Encoder.forward end to end on the device (trunk included) stays within TF32 noise of the same values
         f2, d2 = enc(img.to(DEV))
         assert (f2 - feat).abs().max() <= 2e-2 * feat.abs().max()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 40, 40), (2, 30, 44), (1, 200, 200), (3, 100, 100)])
+def test_aspp_fused_kernel_vs_oracle(B, H, W, monkeypatch):
+    """DeepLabHead(64 -> 64, hidden 128) with the ASPP branches + projection as ONE back-to-back kernel
+    (stp3_aspp_fused_fwd) against the fp64 oracle and against the unfused launch sequence: dilation 12 / 24 / 36 taps live
+    at 200x200, skipped padding taps and ragged edge tiles at the small sizes."""
+    monkeypatch.setenv("STP3_ASPP_FUSED", "1")
+    with torch.no_grad():
+        head = TD.init_exact(DeepLabHead(64, 64, hidden_channel=128), seed=17).eval()
+        x = dense_input((B, 64, H, W), 18)
+        ref = TD.deeplab_head(x.double(), f64(head))
+        y = head.to(DEV)(x.to(DEV))
+        assert "fused" in head.packed()
+        err = close(y, ref)
+        monkeypatch.setenv("STP3_ASPP_FUSED", "0")
+        head2 = TD.init_exact(DeepLabHead(64, 64, hidden_channel=128), seed=17).eval().to(DEV)
+        y2 = head2(x.to(DEV))
+        assert "fused" not in head2.packed()
+        assert (y - y2).abs().max() <= 2e-5 * y2.abs().max(), "fused and unfused ASPP disagree"
+    print(f"aspp fused {B}x{H}x{W}: {err:.2e} of max vs fp64 oracle")
