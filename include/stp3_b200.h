@@ -212,6 +212,8 @@ typedef struct stp3_aspp_desc {
   int n_taps[4];              /* 1 .. 9 each; every branch must contain its centre tap (0, 0) */
   signed char taps[4][9][2];  /* (dy, dx) input offsets */
   int out_cstride, out_coff;
+  int no_relu;                /* 0: ReLU on the projection output (ASPP); 1: none (3x3 conv -> 1x1 classifier tail) */
+  int n_store;                /* output channels written: 128 (0 = default) or 64 (projection rows 64.. are zero padding) */
 } stp3_aspp_desc;
 int stp3_aspp_fused_fwd(const stp3_aspp_desc* desc, const void* x_hi, const void* x_lo, const void* w,
                         const float* br_bias, const float* img_bias, void* y_hi, void* y_lo, void* stream);

@@ -33,7 +33,8 @@ class ConvDesc(ctypes.Structure):
 class AsppDesc(ctypes.Structure):
     """Mirror of stp3_aspp_desc (include/stp3_b200.h)."""
     _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("in_cstride", _I), ("cin", _I), ("n_br", _I),
-                ("n_taps", _I * 4), ("taps", ((ctypes.c_byte * 2) * 9) * 4), ("out_cstride", _I), ("out_coff", _I)]
+                ("n_taps", _I * 4), ("taps", ((ctypes.c_byte * 2) * 9) * 4), ("out_cstride", _I), ("out_coff", _I),
+                ("no_relu", _I), ("n_store", _I)]
 
 
 class ConvHead(ctypes.Structure):

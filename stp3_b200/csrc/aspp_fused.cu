@@ -10,12 +10,16 @@
 //                         acc2 += P . W_proj[:, b-th 128 input channels]   (second MMA chain, A operand = P)
 //   out = hi/lo split of relu(acc2 + per-image bias)                       (the global-pool branch is that bias)
 //
+// The same kernel runs the head's tail, 3x3 conv/BN/ReLU -> 1x1 classifier (convolutions.py:272-280), as a ONE-branch
+// instance (9 taps, two input K blocks, classifier rows padded to 128, no ReLU on the output).
+//
 // Same precision scheme as conv_tcgen05.cu (bf16 hi/lo planes, hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), so the
 // result matches the unfused path to the last few bits of the split.
 //
 //   warps : 0 = TMA producer (activation ring + weight ring, both CTAs), 1 = MMA issuer (leader CTA), 2..9 = epilogue
-//   MMA order per tile: main(0), main(1), proj(0), main(2), proj(1), main(3), proj(2), proj(3) -- the projection of branch
-//   b is issued after the main loop of branch b+1, so the tensor pipe works on b+1 while the epilogue converts b
+//   MMA order: main(0), main(1), proj(0), main(2), proj(1), main(3), proj(2), main(0 of the next tile), proj(3), ... -- the
+//   projection of a (tile, branch) unit is issued after the main loop of the NEXT unit, so the tensor pipe works on that
+//   while the epilogue converts the finished one
 //   TMEM  : acc1 double-buffered (2 x 128 columns), acc2 128 columns
 //   smem  : 3 activation stages (32 KB) + 3 weight stages (16 KB) + P (2 K-blocks x hi/lo x 16 KB = 64 KB) = 208 KB
 #include <cuda_bf16.h>
@@ -46,6 +50,8 @@ struct AsppParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   int out_cstride, out_coff;
+  int relu_out;                                   // ReLU on the projection output (ASPP: yes; conv3 -> classifier: no)
+  int n_store;                                    // output channels stored (64 or 128): rows >= n_store of the projection are zero
 };
 
 __device__ __forceinline__ bool aspp_tap_is_padding(const AsppParams& p, int t, int oy_tile, int ox0) {
@@ -121,33 +127,34 @@ aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       __syncwarp();
       if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
     };
+    int pend = -1;                                 // branch whose projection weights follow the next main loop's
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
       const int oy_tile = (rem / p.tiles_x) * 16, ox0 = (rem % p.tiles_x) * 16;
       const int oy0 = oy_tile + (int)rank * 8;
       const int bidx = img / p.T, tidx = img % p.T;
-      for (int s = 0; s <= p.n_br; ++s) {
-        if (s < p.n_br) {
-          for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
-            if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              ptx::mbar_wait(&a_empty[as], aph ^ 1);
-              if (ptx::elect_one_sync()) {
-                unsigned char* sa = a_ring + (size_t)as * kAStage;
-                const uint32_t bar = ptx::mapa(ptx::smem_u32(&a_full[as]), 0);
-                ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)kAStage);
-                ptx::tma_load_5d_pair(sa, &tm_a_hi, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
-                ptx::tma_load_5d_pair(sa + kAStage / 2, &tm_a_lo, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
-              }
-              __syncwarp();
-              if (++as == kAsppNA) { as = 0; aph ^= 1; }
-              load_b(t * p.kblocks + kb);
+      for (int s = 0; s < p.n_br; ++s) {
+        for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
+          if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&a_empty[as], aph ^ 1);
+            if (ptx::elect_one_sync()) {
+              unsigned char* sa = a_ring + (size_t)as * kAStage;
+              const uint32_t bar = ptx::mapa(ptx::smem_u32(&a_full[as]), 0);
+              ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)kAStage);
+              ptx::tma_load_5d_pair(sa, &tm_a_hi, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
+              ptx::tma_load_5d_pair(sa + kAStage / 2, &tm_a_lo, bar, kb * 64, ox0 + p.tap[t][1], oy0 + p.tap[t][0], tidx, bidx);
             }
+            __syncwarp();
+            if (++as == kAsppNA) { as = 0; aph ^= 1; }
+            load_b(t * p.kblocks + kb);
           }
         }
-        if (s >= 1) { load_b(proj_blk0 + (s - 1) * 2); load_b(proj_blk0 + (s - 1) * 2 + 1); }   // projection weights of branch s-1
+        if (pend >= 0) { load_b(proj_blk0 + pend * 2); load_b(proj_blk0 + pend * 2 + 1); }   // projection weights of the previous unit
+        pend = s;
       }
     }
+    if (pend >= 0) { load_b(proj_blk0 + pend * 2); load_b(proj_blk0 + pend * 2 + 1); }
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader) =====================
     const uint32_t idesc = ptx::umma_idesc_bf16(256, kAsppHidden);
@@ -164,70 +171,72 @@ aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         ptx::umma_bf16_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, 1);
       }
     };
+    const uint32_t tmem_d2 = tmem_base + 2u * kAsppHidden;
+    // proj(j): acc2 (+)= P . W_proj[:, branch j]; issued one unit late (after the NEXT main loop, also across tiles), so the
+    // tensor pipe never waits for the epilogue's conversion of the unit it has just finished
+    auto proj = [&](int j) {
+      if (j == 0) {                                // the previous tile's output has left acc2
+        ptx::mbar_wait(acc2_empty, t2ph ^ 1);
+        ptx::tc_fence_after();
+      }
+      for (int kb2 = 0; kb2 < 2; ++kb2) {
+        ptx::mbar_wait(&p_full[kb2], pph);
+        ptx::mbar_wait(&b_full[bs], bph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one_sync()) {
+          const uint32_t a_hi = ptx::smem_u32(p_buf + (size_t)kb2 * 2 * kPPlane);
+          const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBStage);
+          issue(tmem_d2, a_hi, a_hi + kPPlane, b_hi, b_hi + 64 * 128, (j > 0 || kb2 > 0) ? 1u : 0u);
+          ptx::umma_commit_pair(&b_empty[bs]);
+          ptx::umma_commit_pair(&p_empty[kb2]);
+        }
+        __syncwarp();
+        if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
+      }
+      pph ^= 1;
+      if (j == p.n_br - 1) {
+        if (ptx::elect_one_sync()) ptx::umma_commit_pair(acc2_full);
+        __syncwarp();
+        t2ph ^= 1;
+      }
+    };
+    int pend = -1;
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int rem = tile % tiles_per_img;
       const int oy_tile = (rem / p.tiles_x) * 16, ox0 = (rem % p.tiles_x) * 16;
-      for (int s = 0; s <= p.n_br; ++s) {
-        if (s < p.n_br) {
-          // ---- main(s): acc1[buf1] = sum over the branch's taps
-          ptx::mbar_wait(&acc1_empty[buf1], acc1_ph ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(buf1 * kAsppHidden);
-          uint32_t accumulate = 0;
-          for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
-            if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              ptx::mbar_wait(&a_full[as], aph);
-              ptx::mbar_wait(&b_full[bs], bph);
-              ptx::tc_fence_after();
-              if (ptx::elect_one_sync()) {
-                const uint32_t a_hi = ptx::smem_u32(a_ring + (size_t)as * kAStage);
-                const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBStage);
-                issue(tmem_d, a_hi, a_hi + kAStage / 2, b_hi, b_hi + 64 * 128, accumulate);
-                ptx::umma_commit_pair(&b_empty[bs]);
-                ptx::umma_commit_pair(&a_empty[as]);
-              }
-              __syncwarp();
-              accumulate = 1;
-              if (++as == kAsppNA) { as = 0; aph ^= 1; }
-              if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
-            }
-          }
-          if (ptx::elect_one_sync()) ptx::umma_commit_pair(&acc1_full[buf1]);
-          __syncwarp();
-          if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
-        }
-        if (s >= 1) {
-          // ---- proj(s-1): acc2 += P . W_proj[:, branch s-1]
-          const int j = s - 1;
-          if (j == 0) {                            // the previous tile's output has left acc2
-            ptx::mbar_wait(acc2_empty, t2ph ^ 1);
-            ptx::tc_fence_after();
-          }
-          const uint32_t tmem_d2 = tmem_base + 2u * kAsppHidden;
-          for (int kb2 = 0; kb2 < 2; ++kb2) {
-            ptx::mbar_wait(&p_full[kb2], pph);
+      for (int s = 0; s < p.n_br; ++s) {
+        // ---- main(s): acc1[buf1] = sum over the branch's taps
+        ptx::mbar_wait(&acc1_empty[buf1], acc1_ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf1 * kAsppHidden);
+        uint32_t accumulate = 0;
+        for (int t = p.br_tap0[s]; t < p.br_tap0[s + 1]; ++t) {
+          if (aspp_tap_is_padding(p, t, oy_tile, ox0)) continue;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&a_full[as], aph);
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             if (ptx::elect_one_sync()) {
-              const uint32_t a_hi = ptx::smem_u32(p_buf + (size_t)kb2 * 2 * kPPlane);
+              const uint32_t a_hi = ptx::smem_u32(a_ring + (size_t)as * kAStage);
               const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBStage);
-              issue(tmem_d2, a_hi, a_hi + kPPlane, b_hi, b_hi + 64 * 128, (j > 0 || kb2 > 0) ? 1u : 0u);
+              issue(tmem_d, a_hi, a_hi + kAStage / 2, b_hi, b_hi + 64 * 128, accumulate);
               ptx::umma_commit_pair(&b_empty[bs]);
-              ptx::umma_commit_pair(&p_empty[kb2]);
+              ptx::umma_commit_pair(&a_empty[as]);
             }
             __syncwarp();
+            accumulate = 1;
+            if (++as == kAsppNA) { as = 0; aph ^= 1; }
             if (++bs == kAsppNB) { bs = 0; bph ^= 1; }
           }
-          pph ^= 1;
-          if (j == p.n_br - 1) {
-            if (ptx::elect_one_sync()) ptx::umma_commit_pair(acc2_full);
-            __syncwarp();
-            t2ph ^= 1;
-          }
         }
+        if (ptx::elect_one_sync()) ptx::umma_commit_pair(&acc1_full[buf1]);
+        __syncwarp();
+        if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
+        if (pend >= 0) proj(pend);
+        pend = s;
       }
     }
+    if (pend >= 0) proj(pend);
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int e = warp - 2;
@@ -301,12 +310,13 @@ aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         uint32_t acc[16];
         ptx::tmem_ld_32x32b_x16(tmem_acc2 + j * 16, acc);
         ptx::tmem_ld_wait();
-        if (valid) {
+        if (valid && col0 + j * 16 < p.n_store) {
           uint32_t hw[8], lw[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float x0 = fmaxf(__uint_as_float(acc[2 * i]) + wb[j * 16 + 2 * i], 0.f);
-            const float x1 = fmaxf(__uint_as_float(acc[2 * i + 1]) + wb[j * 16 + 2 * i + 1], 0.f);
+            float x0 = __uint_as_float(acc[2 * i]) + wb[j * 16 + 2 * i];
+            float x1 = __uint_as_float(acc[2 * i + 1]) + wb[j * 16 + 2 * i + 1];
+            if (p.relu_out) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
             const uint32_t h = ptx::pack_bf16x2(x0, x1);
             hw[i] = h;
             lw[i] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
@@ -353,9 +363,11 @@ extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, co
   STP3_CHECK_ARG(d->B > 0 && d->T > 0 && d->H > 0 && d->W > 0, "non-positive dimension");
   STP3_CHECK_ARG(d->in_cstride % 64 == 0 && d->cin % 64 == 0 && d->cin > 0 && d->cin <= d->in_cstride, "input channels: multiples of 64");
   STP3_CHECK_ARG(d->n_br >= 1 && d->n_br <= kAsppMaxBranches, "1 .. 4 branches");
-  STP3_CHECK_ARG(d->out_cstride % 16 == 0 && d->out_coff % 16 == 0 && d->out_coff + kAsppHidden <= d->out_cstride &&
+  const int n_store = d->n_store > 0 ? d->n_store : kAsppHidden;
+  STP3_CHECK_ARG(n_store == 64 || n_store == 128, "n_store must be 64 or 128");
+  STP3_CHECK_ARG(d->out_cstride % 16 == 0 && d->out_coff % 16 == 0 && d->out_coff + n_store <= d->out_cstride &&
                  (reinterpret_cast<uintptr_t>(y_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(y_lo) & 31) == 0,
-                 "output planes: 128 channels at a 16-channel aligned offset, 32-byte aligned");
+                 "output planes: n_store channels at a 16-channel aligned offset, 32-byte aligned");
   PFN_tmapEncodeTiledA enc = aspp_encode_fn();
   if (!enc) return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   AsppParams p;
@@ -380,6 +392,7 @@ extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, co
   p.br_bias = br_bias; p.img_bias = img_bias;
   p.out_hi = static_cast<__nv_bfloat16*>(y_hi); p.out_lo = static_cast<__nv_bfloat16*>(y_lo);
   p.out_cstride = d->out_cstride; p.out_coff = d->out_coff;
+  p.relu_out = d->no_relu ? 0 : 1; p.n_store = n_store;
 
   CUtensorMap tm_hi, tm_lo, tm_w;
   {

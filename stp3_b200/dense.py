@@ -268,9 +268,15 @@ class PackedAspp:
 
 
 def pack_aspp(branches, proj_w: torch.Tensor, proj_b: torch.Tensor) -> PackedAspp:
-    """branches: [(weight (128, Cin, kh, kw) BN-folded, bias (128), dilation)]; proj_w (128, n_br * 128) BN-folded.
-    Layout of stp3_aspp_fused_fwd (include/stp3_b200.h)."""
+    """branches: [(weight (128, Cin, kh, kw) BN-folded, bias (128), dilation)]; proj_w (<= 128, n_br * 128) BN-folded
+    (fewer than 128 output rows are zero-padded).  Layout of stp3_aspp_fused_fwd (include/stp3_b200.h)."""
     h = 128
+    if proj_w.shape[0] < h:
+        pw = torch.zeros((h, proj_w.shape[1]), dtype=proj_w.dtype, device=proj_w.device)
+        pw[:proj_w.shape[0]] = proj_w
+        pb = torch.zeros(h, dtype=proj_b.dtype, device=proj_b.device)
+        pb[:proj_b.shape[0]] = proj_b
+        proj_w, proj_b = pw, pb
     cin = branches[0][0].shape[1]
     cin_p = pad_to(cin)
     kbs = cin_p // KB
@@ -299,11 +305,13 @@ def pack_aspp(branches, proj_w: torch.Tensor, proj_b: torch.Tensor) -> PackedAsp
     return PackedAspp(packed, torch.stack(biases).float().contiguous(), proj_b.float().contiguous(), taps_all, cin_p)
 
 
-def aspp_fused(x: HL, pa: PackedAspp, img_bias: torch.Tensor, out: Optional[HL] = None, out_coff: int = 0) -> HL:
-    """y = relu(project(cat_b relu(branch_b(x))) + img_bias): stp3_aspp_fused_fwd."""
+def aspp_fused(x: HL, pa: PackedAspp, img_bias: torch.Tensor, out: Optional[HL] = None, out_coff: int = 0,
+               relu: bool = True, n_store: int = 128, c_out: Optional[int] = None) -> HL:
+    """y = [relu](project(cat_b relu(branch_b(x))) + img_bias): stp3_aspp_fused_fwd.  n_store = 64: only the first 64
+    output channels exist (c_out of them real)."""
     B, T, H, W, cs = x.hi.shape
     if out is None:
-        out = HL.empty(B, T, H, W, 128, x.hi.device, cp=128)
+        out = HL.empty(B, T, H, W, c_out or n_store, x.hi.device, cp=n_store)
     assert img_bias.shape == (B * T, 128) and img_bias.dtype == torch.float32 and img_bias.is_contiguous()
     d = _lib.AsppDesc()
     d.B, d.T, d.H, d.W, d.in_cstride, d.cin = B, T, H, W, cs, pa.cin_p
@@ -313,6 +321,7 @@ def aspp_fused(x: HL, pa: PackedAspp, img_bias: torch.Tensor, out: Optional[HL] 
         for i, (dy, dx) in enumerate(taps):
             d.taps[b][i][0], d.taps[b][i][1] = dy, dx
     d.out_cstride, d.out_coff = out.hi.shape[-1], out_coff
+    d.no_relu, d.n_store = int(not relu), n_store
     with torch.cuda.device(x.hi.device):
         code = _lib.lib().stp3_aspp_fused_fwd(ctypes.byref(d), x.hi.data_ptr(), x.lo.data_ptr(), pa.w.data_ptr(),
                                               pa.br_bias.data_ptr(), img_bias.data_ptr(), out.hi.data_ptr(),

@@ -104,7 +104,7 @@ class DeepLabHead(nn.Sequential, PackedModule):
         P["cls"] = dense.pack_conv(self[4].weight.detach().float(), self[4].bias.detach().float())
         P["nb"] = nb
         # hidden = 128, dilations that fit signed-byte taps: branches + projection as one back-to-back kernel
-        if h == 128 and nb <= 4 and max(aspp.rates) <= 127 and os.environ.get("STP3_ASPP_FUSED", "0") != "0":
+        if h == 128 and nb <= 4 and max(aspp.rates) <= 127 and os.environ.get("STP3_ASPP_FUSED", "1") != "0":
             br = []
             w, b = dense.fold_bn(aspp.convs[0][0].weight, aspp.convs[0][1])
             br.append((w, b, 1))
@@ -112,6 +112,12 @@ class DeepLabHead(nn.Sequential, PackedModule):
                 w, b = dense.fold_bn(aspp.convs[1 + i][0].weight, aspp.convs[1 + i][1])
                 br.append((w, b, r))
             P["fused"] = dense.pack_aspp(br, wproj[:, :nb * h].reshape(h, nb * h), bproj)
+            if self.num_classes <= 64:
+                # the tail 3x3 conv/BN/ReLU -> 1x1 classifier through the same back-to-back kernel (one branch): the
+                # 128-channel intermediate stays on chip
+                w3, b3 = dense.fold_bn(self[1].weight, self[2])
+                P["tail"] = dense.pack_aspp([(w3, b3, 1)], self[4].weight.detach().float().reshape(self.num_classes, h),
+                                            self[4].bias.detach().float())
         return P
 
     def forward_hl(self, x: dense.HL, out: Optional[dense.HL] = None, sums: Optional[torch.Tensor] = None) -> dense.HL:
@@ -134,6 +140,10 @@ class DeepLabHead(nn.Sequential, PackedModule):
             for i in range(nb):
                 dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
             y = dense.conv(cat, P["proj"], relu=True, img_bias=pbias)   # Dropout(0.5) is the identity in eval mode
+        if "tail" in P and out is None:
+            n_img = B * T
+            bias = P["tail"].proj_bias.unsqueeze(0).expand(n_img, -1).contiguous()
+            return dense.aspp_fused(y, P["tail"], bias, relu=False, n_store=64, c_out=self.num_classes)
         y = dense.conv(y, P["conv3"], relu=True)
         return dense.conv(y, P["cls"], out=out)
 
