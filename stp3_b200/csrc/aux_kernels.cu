@@ -119,24 +119,44 @@ __global__ void pool_bias_kernel(const float* __restrict__ sums, int sums_stride
     m[c] = s / cnt;
   }
   __syncthreads();
-  // one warp per output row, lanes stride over the inputs (the serial per-thread dot products were latency-bound)
+  // one warp per output row, lanes stride over the inputs; four rows in flight per warp so that their (cold, L2 / HBM)
+  // weight loads overlap -- the kernel sits on the critical path between two convolutions and is pure latency
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nwarps) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(W1[(size_t)r * C + c], m[c], a);
+  for (int r0 = warp * 4; r0 < R; r0 += nwarps * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < C; c += 32) {
+      const float mc = m[c];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) v[r] = fmaxf(a + b1[r], 0.f);
+      for (int i = 0; i < 4; ++i)
+        if (r0 + i < R) a[i] = fmaf(__ldg(W1 + (size_t)(r0 + i) * C + c), mc, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+      if (lane == 0 && r0 + i < R) v[r0 + i] = fmaxf(a[i] + b1[r0 + i], 0.f);
+    }
   }
   __syncthreads();
-  for (int co = warp; co < CO; co += nwarps) {
-    float a = 0.f;
-    for (int r = lane; r < R; r += 32) a = fmaf(W2[(size_t)co * R + r], v[r], a);
+  // blockIdx.y owns a slice of the output rows (every slice recomputes the small hidden vector v)
+  const int co_per = (CO + gridDim.y - 1) / gridDim.y;
+  const int co_begin = blockIdx.y * co_per, co_end = min(CO, co_begin + co_per);
+  for (int co0 = co_begin + warp * 4; co0 < co_end; co0 += nwarps * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = lane; r < R; r += 32) {
+      const float vr = v[r];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      float* dst = out + (size_t)img * co_stride + co;
-      *dst = (accumulate ? *dst : (bias ? bias[co] : 0.f)) + a;
+      for (int i = 0; i < 4; ++i)
+        if (co0 + i < co_end) a[i] = fmaf(__ldg(W2 + (size_t)(co0 + i) * R + r), vr, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+      if (lane == 0 && co0 + i < co_end) {
+        float* dst = out + (size_t)img * co_stride + co0 + i;
+        *dst = (accumulate ? *dst : (bias ? bias[co0 + i] : 0.f)) + a[i];
+      }
     }
   }
 }
@@ -266,7 +286,7 @@ extern "C" int stp3_pool_bias(const float* sums, int sums_stride, int n_img, int
   STP3_CHECK_ARG(sums && W1 && b1 && W2 && out && n_img > 0 && T > 0 && C > 0 && R > 0 && CO > 0 && n_const >= 0 &&
                  n_const < C && C - n_const <= sums_stride && CO <= co_stride && (n_const == 0 || const_vals),
                  "stp3_pool_bias: bad argument");
-  STP3_CUDA_OK(launch_pdl(pool_bias_kernel, dim3(n_img), dim3(256), (size_t)(C + R) * sizeof(float), (cudaStream_t)stream,
+  STP3_CUDA_OK(launch_pdl(pool_bias_kernel, dim3(n_img, CO >= 64 ? 4 : 1), dim3(256), (size_t)(C + R) * sizeof(float), (cudaStream_t)stream,
                           sums, sums_stride, T, C, inv_hw, temporal, const_vals, n_const, W1, b1, R, W2, CO, bias, out,
                           co_stride, accumulate));
   return STP3_OK;

@@ -31,11 +31,12 @@ def conv(rep, dst):
     trd = twr = tt = 0.0
     for i, r in enumerate(data):
         name = r[idx["Kernel Name"]]
-        short = name.split("conv_igemm_kernel")[1].split("(")[0] if "conv_igemm" in name else name[:20]
+        short = name.split("conv_igemm_kernel")[1].split("(")[0] if "conv_igemm" in name else \
+            ("  aspp_fused" if "aspp_fused" in name else name[:20])
         t = num(r, idx, "gpu__time_duration.sum")
         rd, wr = num(r, idx, "dram__bytes_read.sum"), num(r, idx, "dram__bytes_write.sum")
         l2 = num(r, idx, "lts__t_sectors_srcunit_tex_op_read.sum") * 32 / 1e9
-        L.append(f"{i:2d} conv_igemm{short:14s} {r[idx['launch__grid_size']]:>5} {t:8.1f} {rd:10.1f} {wr:10.1f} {l2:10.2f} "
+        L.append(f"{i:2d} {'conv_igemm' if 'conv_igemm' in name else '          '}{short:14s} {r[idx['launch__grid_size']]:>5} {t:8.1f} {rd:10.1f} {wr:10.1f} {l2:10.2f} "
                  f"{l2 / t * 1e3:12.2f} {r[idx['launch__registers_per_thread']]:>5}")
         trd += rd; twr += wr; tt += t
     L.append(f"units: {units[idx['gpu__time_duration.sum']]}, {units[idx['dram__bytes_read.sum']]}")
