@@ -256,7 +256,8 @@ aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const float* ib = p.img_bias + (size_t)img * kAsppHidden + col0;
         float* wb = s_wb + e * 64;
         __syncwarp();
-        wb[lane] = __ldg(ib + lane); wb[lane + 32] = __ldg(ib + lane + 32);
+        const volatile float* ibv = ib;            // written by the preceding (PDL-overlapped) pool_bias kernel: coherent loads
+        wb[lane] = ibv[lane]; wb[lane + 32] = ibv[lane + 32];
         __syncwarp();
       }
       for (int b = 0; b < p.n_br; ++b) {

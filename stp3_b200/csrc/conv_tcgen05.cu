@@ -430,14 +430,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int oy = oy_t + sub * kSubH + (r >> 4);
         if (oy < p.Ho && ox < p.Wo) {
           const size_t off = (((size_t)img * p.Ho + oy) * p.Wo + ox) * p.res_cstride + p.res_coff + col0 + j * 16;
+          // coherent loads: the residual (like the per-image bias below) is written by a PRECEDING kernel that this grid
+          // may overlap under programmatic dependent launch, so the read-only (.nc) path is not allowed for it
           if (p.vec256 & 2) {
-            ptx::ld_global_nc_v8(p.res_hi + off, nh);
-            ptx::ld_global_nc_v8(p.res_lo + off, nl);
+            ptx::ld_global_v8(p.res_hi + off, nh);
+            ptx::ld_global_v8(p.res_lo + off, nl);
           } else {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + g);
-              const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + g);
+              const uint4 h4 = ptx::ld_global_v4(reinterpret_cast<const uint4*>(p.res_hi + off) + g);
+              const uint4 l4 = ptx::ld_global_v4(reinterpret_cast<const uint4*>(p.res_lo + off) + g);
               nh[4 * g] = h4.x; nh[4 * g + 1] = h4.y; nh[4 * g + 2] = h4.z; nh[4 * g + 3] = h4.w;
               nl[4 * g] = l4.x; nl[4 * g + 1] = l4.y; nl[4 * g + 2] = l4.z; nl[4 * g + 3] = l4.w;
             }
@@ -451,7 +453,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         float* wb = s_wb + e * 64;
         __syncwarp();                             // every lane is done with the previous tile's slice
 #pragma unroll
-        for (int i = lane; i < kColsPerWarp; i += 32) wb[i] = __ldg(ib + i);
+        for (int i = lane; i < kColsPerWarp; i += 32) wb[i] = *(reinterpret_cast<const volatile float*>(ib) + i);
         __syncwarp();
         bsrc = wb - col0;
       }

@@ -27,6 +27,11 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) { 
                : "l"(p)
                : "memory");
 }
+__device__ __forceinline__ uint4 ld_global_v4(const void* p) {                        // coherent 128-bit load
+  uint4 r;
+  asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])

@@ -80,6 +80,10 @@ class PackedConv:
     stride: int
     k_lo: int = 0              # input channels [k_lo, k_hi) of the window carry weights (multiples of 16)
     k_hi: int = 0
+    uid: int = 0               # identity of this packing for the autotune cache (a data_ptr can be reused after a repack)
+
+
+_PACK_COUNTER = 0
 
 
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dilation: int = 1,
@@ -128,7 +132,9 @@ def pack_conv(weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, dila
     k_hi = (max(off + n for _, n, off in in_layout) + 15) // 16 * 16
     if not (k_lo < KB and k_hi > cin_p - KB):          # the kernel trims only the first / last 64-channel block
         k_lo, k_hi = 0, cin_p
-    return PackedConv(packed, b, taps, cin_p, bn, cout, stride, k_lo, k_hi)
+    global _PACK_COUNTER
+    _PACK_COUNTER += 1
+    return PackedConv(packed, b, taps, cin_p, bn, cout, stride, k_lo, k_hi, _PACK_COUNTER)
 
 
 # ------------------------------------------------------------------------------------------------ autotuner
@@ -245,7 +251,7 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
                 ctypes.byref(hd) if hd is not None else None, torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(code, "stp3_conv_fwd")
 
-    key = (pc.w.data_ptr(), B, T, H, W, cs, cin_off, Ho, Wo, t0, int(relu), residual is not None, out_f32 is not None,
+    key = (pc.uid, B, T, H, W, cs, cin_off, Ho, Wo, t0, int(relu), residual is not None, out_f32 is not None,
            hd is not None, out2 is not None)
     cfg = tune if tune is not None else _TUNED.get(key)
     if cfg is None and _AUTOTUNE and not torch.cuda.is_current_stream_capturing():
@@ -253,6 +259,10 @@ def conv(x: HL, pc: PackedConv, *, cin_off: int = 0, out: Optional[HL] = None, o
         groupable = any(taps[i + 1][0] == taps[i][0] and taps[i + 1][2] == taps[i][2] and
                         taps[i + 1][1] == taps[i][1] + pc.stride for i in range(len(taps) - 1))
         desc = f"{len(taps)}tap cin{pc.cin_p} bn{pc.bn} s{pc.stride} {B * T}x{Ho}x{Wo}"
+        # the tuner launches the layer many times: an output that aliases an input would be corrupted silently
+        ins = {x.hi.data_ptr(), x.lo.data_ptr()} | ({residual.hi.data_ptr(), residual.lo.data_ptr()} if residual is not None else set())
+        outs = {t.data_ptr() for t in ((out.hi, out.lo) if out is not None else ()) + ((out2.hi, out2.lo) if out2 is not None else ())}
+        assert not (ins & outs), "stp3_b200.dense.conv: output aliases an input (in-place convolution is not supported)"
         cfg = _tune(key, desc, launch, groupable, len(taps), pc.bn)
     launch(*(cfg or (0, 0)))
     return out

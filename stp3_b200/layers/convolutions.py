@@ -141,9 +141,10 @@ class DeepLabHead(nn.Sequential, PackedModule):
                 dense.conv(x, P[f"b{i}"], out=cat, out_coff=i * h, relu=True)
             y = dense.conv(cat, P["proj"], relu=True, img_bias=pbias)   # Dropout(0.5) is the identity in eval mode
         if "tail" in P and out is None:
-            n_img = B * T
-            bias = P["tail"].proj_bias.unsqueeze(0).expand(n_img, -1).contiguous()
-            return dense.aspp_fused(y, P["tail"], bias, relu=False, n_store=64, c_out=self.num_classes)
+            key = ("tail_bias", B * T)
+            if key not in P:                   # the classifier's bias as a (constant) per-image table, built once
+                P[key] = P["tail"].proj_bias.unsqueeze(0).expand(B * T, -1).contiguous()
+            return dense.aspp_fused(y, P["tail"], P[key], relu=False, n_store=64, c_out=self.num_classes)
         y = dense.conv(y, P["conv3"], relu=True)
         return dense.conv(y, P["cls"], out=out)
 
