@@ -39,6 +39,14 @@ class STP3(nn.Module):
         if self.n_future > 0 or cfg.PLANNING.ENABLED:
             raise NotImplementedError("stp3_b200 implements the perception hot path (N_FUTURE_FRAMES=0, PLANNING "
                                       "disabled); prediction / planning are out of scope (SURVEY.md §2, rows 12-13)")
+        if self.encoder_out_channels % 64 != 0:
+            raise NotImplementedError(f"MODEL.ENCODER.OUT_CHANNELS = {self.encoder_out_channels}: the tensor-core layers carry "
+                                      "channels in blocks of 64 (the reference's configs use 64; the stress configuration 128)")
+        if cfg.MODEL.TEMPORAL_MODEL.NAME == 'temporal_block' and cfg.MODEL.TEMPORAL_MODEL.INBETWEEN_LAYERS != 0:
+            raise NotImplementedError("MODEL.TEMPORAL_MODEL.INBETWEEN_LAYERS > 0 (Bottleneck3D, temporal.py:328-372) is not used "
+                                      "by any reference config and is not built")
+        if cfg.TIME_RECEPTIVE_FIELD > 8:
+            raise NotImplementedError("TIME_RECEPTIVE_FIELD > 8: the lift-splat keeps the ego-motion chain of at most 8 frames")
         self.spatial_extent = (cfg.LIFT.X_BOUND[1], cfg.LIFT.Y_BOUND[1])
         self.bev_size = (int(dim[0]), int(dim[1]))
 
