@@ -219,6 +219,42 @@ int stp3_aspp_fused_fwd(const stp3_aspp_desc* desc, const void* x_hi, const void
                         const float* br_bias, const float* img_bias, void* y_hi, void* y_lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Tail of a TemporalBlock (stp3/layers/temporal.py:426-489) as ONE back-to-back tensor-core kernel:
+ *   out = relu(BN(aggregation 1x1x1 of [path 0 | path 1 | path 2 | pyramid pooling])) + (projection(x) | x)
+ * with path 0 / 1 = the causal (2,3,3) / (1,3,3) convolutions of the entry convolutions' outputs `mid` and path 2 = a
+ * 1x1x1 convolution of x.  Up to three MMA chains accumulate the paths side by side in TMEM, the activated concat is
+ * converted to bf16 hi/lo in shared memory and multiplied with the aggregation weights; the 128-channel concat tensor
+ * never exists.  Applicable when every path has <= 48 channels, x <= 64 spatial channels and the block <= 64 outputs.
+ *   chain: src (0 = mid, 1 = x), cin_off (64-channel K block read), taps (dt, dy, dx), n_mma (MMA width, multiple of 16),
+ *          tmem_col (column of its first output in the hidden accumulator, multiple of 16), [k_lo, k_hi) channels with data
+ *   piece_col[pp]: hidden-accumulator column of the 8-channel piece pp of the 128-channel operand P (-1 = zeros)
+ *   w: bf16 rows of 64, blocks of [hi: 128 rows][lo: 128 rows]; one block per tap of chain 0, 1, 2, then two blocks of the
+ *      aggregation weights (K blocks of P), then one of the projection; output channel n of an N-wide chain sits in row
+ *      n (n < N/2) or 64 + n - N/2 (the two CTAs of a pair each load 64 rows)
+ *   hid_bias [B*T][128] (P order), img_bias [B*T][64] (aggregation bias + pooling branch), res_bias [B*T][64] or NULL
+ *   col_sums optional (B*T, 64): per-image sums over pixels of the output; scratch: stp3_block_fused_scratch_bytes(B*T)
+ */
+typedef struct stp3_block_chain {
+  int src, cin_off, n_taps;
+  signed char taps[18][3];
+  int n_mma, tmem_col, k_lo, k_hi;
+} stp3_block_chain;
+typedef struct stp3_block_desc {
+  int B, T, H, W;
+  int mid_cstride, x_cstride, out_cstride;
+  int n_chain;
+  stp3_block_chain chain[3];
+  int has_res_proj;           /* 1: residual = 1x1 projection of x (chain `res`, 64 outputs); 0: residual = x itself */
+  stp3_block_chain res;
+  int piece_col[16];
+} stp3_block_desc;
+size_t stp3_block_fused_scratch_bytes(int n_img);
+int stp3_block_fused_fwd(const stp3_block_desc* desc, const void* mid_hi, const void* mid_lo, const void* x_hi,
+                         const void* x_lo, const void* w, const float* hid_bias, const float* img_bias,
+                         const float* res_bias, void* y_hi, void* y_lo, float* col_sums, void* scratch,
+                         size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Memory-bound helpers of the dense path (all tensors channels-last bf16 hi/lo planes unless noted).
  */
 /* fp32 (n_img,C,H,W) [channels_last=0, the reference's NCHW] or (n_img,H,W,C) [1] -> hi/lo (n_img,H,W,cp), padding 0.

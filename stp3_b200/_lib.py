@@ -37,6 +37,18 @@ class AsppDesc(ctypes.Structure):
                 ("no_relu", _I), ("n_store", _I)]
 
 
+class BlockChain(ctypes.Structure):
+    """Mirror of stp3_block_chain (include/stp3_b200.h)."""
+    _fields_ = [("src", _I), ("cin_off", _I), ("n_taps", _I), ("taps", (ctypes.c_byte * 3) * 18), ("n_mma", _I),
+                ("tmem_col", _I), ("k_lo", _I), ("k_hi", _I)]
+
+
+class BlockDesc(ctypes.Structure):
+    """Mirror of stp3_block_desc (include/stp3_b200.h)."""
+    _fields_ = [("B", _I), ("T", _I), ("H", _I), ("W", _I), ("mid_cstride", _I), ("x_cstride", _I), ("out_cstride", _I),
+                ("n_chain", _I), ("chain", BlockChain * 3), ("has_res_proj", _I), ("res", BlockChain), ("piece_col", _I * 16)]
+
+
 class ConvHead(ctypes.Structure):
     """Mirror of stp3_conv_head (include/stp3_b200.h)."""
     _fields_ = [("n_out", _I), ("w", _V), ("b", _V), ("out", _V * 8), ("img_stride", ctypes.c_longlong * 8),
@@ -58,6 +70,8 @@ SIGNATURES = {
     "stp3_upsample2x_add": (_I, [_V, _V, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V, _I, _I, _I, _V]),
     "stp3_lift_splat_frames_fwd": (_I, [_V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I,
                                         _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V, _SZ, _V, _V]),
+    "stp3_block_fused_scratch_bytes": (_SZ, [_I]),
+    "stp3_block_fused_fwd": (_I, [ctypes.POINTER(BlockDesc), _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "stp3_aspp_fused_fwd": (_I, [ctypes.POINTER(AsppDesc), _V, _V, _V, _V, _V, _V, _V, _V]),
     "stp3_lift_splat_bwd_scratch_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "stp3_lift_splat_bwd": (_I, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _FP, _FP, _I, _I, _I, _F,

@@ -28,6 +28,9 @@ int set_error(int code, const char* fmt, ...);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// col_sums[img][c] = fixed-order sum of the (n_part, n_img, 64) partial rows an epilogue wrote (conv_tcgen05.cu)
+int launch_col_sum_reduce(const float* part, int n_part, int n_img, float* out, cudaStream_t stream);
+
 }  // namespace stp3
 
 // Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains; it MUST

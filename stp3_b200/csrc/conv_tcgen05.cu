@@ -677,6 +677,11 @@ static PFN_tmapEncodeTiled encode_fn() {
   return fn;
 }
 
+int launch_col_sum_reduce(const float* part, int n_part, int n_img, float* out, cudaStream_t stream) {
+  STP3_CUDA_OK(launch_pdl(col_sum_reduce_kernel, dim3(n_img), dim3(64, 16), 0, stream, part, n_part, n_img, 64, out));
+  return STP3_OK;
+}
+
 }  // namespace stp3
 
 using namespace stp3;

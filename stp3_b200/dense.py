@@ -340,6 +340,95 @@ def aspp_fused(x: HL, pa: PackedAspp, img_bias: torch.Tensor, out: Optional[HL] 
     return out
 
 
+@dataclass
+class PackedBlockTail:
+    w: torch.Tensor                 # (n_blocks, 2, 128, 64) bf16
+    chains: list                    # [(src, cin_off, taps [(dt,dy,dx)], n_mma, tmem_col, k_lo, k_hi)]
+    res: Optional[tuple]            # the projection chain or None (identity residual)
+    piece_col: List[int]
+
+
+def _pair_rows(m: torch.Tensor) -> torch.Tensor:
+    """(N, 64) weight rows of an N-wide chain -> (128, 64): row n of the first / second half of N at row n / 64 + n - N/2
+    (each CTA of a pair loads 64 rows and multiplies its N/2)."""
+    n = m.shape[0]
+    out = torch.zeros((128, KB), dtype=torch.float32, device=m.device)
+    out[:n // 2] = m[:n // 2]
+    out[64:64 + n - n // 2] = m[n // 2:]
+    return out
+
+
+def pack_block_tail(chains, agg_w: torch.Tensor, res_w: Optional[torch.Tensor], piece_col) -> PackedBlockTail:
+    """chains: [(src, cin_off, weight (cout, cin, kt, kh, kw) BN-folded, k_off, n_mma, tmem_col)] -- cin input channels of
+    the chain sit at channels [k_off, k_off + cin) of its 64-channel K block; agg_w (64, 128) aggregation weights in P
+    order; res_w (64, cs) projection weights or None."""
+    dev = agg_w.device
+    blocks, desc = [], []
+    for src, cin_off, w, k_off, n_mma, tmem_col in chains:
+        cout, cin, kt, kh, kw = w.shape
+        assert cout <= n_mma and k_off + cin <= KB
+        taps = []
+        for it in range(kt):
+            for ix in range(kw):
+                for iy in range(kh):
+                    taps.append((it - (kt - 1), iy - (kh - 1) // 2, ix - (kw - 1) // 2))
+                    m = torch.zeros((n_mma, KB), dtype=torch.float32, device=dev)
+                    m[:cout, k_off:k_off + cin] = w[:, :, it, iy, ix]
+                    blocks.append(_pair_rows(m))
+        desc.append((src, cin_off, taps, n_mma, tmem_col, k_off // 16 * 16, (k_off + cin + 15) // 16 * 16))
+    for kb2 in range(2):
+        blocks.append(_pair_rows(agg_w[:, kb2 * KB:(kb2 + 1) * KB].float()))
+    res = None
+    if res_w is not None:
+        cs = res_w.shape[1]
+        m = torch.zeros((64, KB), dtype=torch.float32, device=dev)
+        m[:res_w.shape[0], :cs] = res_w
+        blocks.append(_pair_rows(m))
+        res = (1, 0, [(0, 0, 0)], 64, 0, 0, (cs + 15) // 16 * 16)
+    hi, lo = split_hilo(torch.stack(blocks))
+    return PackedBlockTail(torch.stack([hi, lo], dim=1).contiguous(), desc, res, list(piece_col))
+
+
+def block_tail(mid: HL, x: HL, pb: PackedBlockTail, hid_bias: torch.Tensor, img_bias: torch.Tensor,
+               res_bias: Optional[torch.Tensor], col_sums: Optional[torch.Tensor] = None) -> HL:
+    """stp3_block_fused_fwd: the paths, the aggregation convolution and the residual of a TemporalBlock in one kernel."""
+    B, T, H, W, _ = x.hi.shape
+    out = HL.empty(B, T, H, W, 64, x.hi.device, cp=64)
+    d = _lib.BlockDesc()
+    d.B, d.T, d.H, d.W = B, T, H, W
+    d.mid_cstride, d.x_cstride, d.out_cstride = mid.hi.shape[-1], x.hi.shape[-1], 64
+
+    def fill(dst, c):
+        src, cin_off, taps, n_mma, tmem_col, k_lo, k_hi = c
+        dst.src, dst.cin_off, dst.n_taps, dst.n_mma, dst.tmem_col, dst.k_lo, dst.k_hi = src, cin_off, len(taps), n_mma, tmem_col, k_lo, k_hi
+        for i, (dt, dy, dx) in enumerate(taps):
+            dst.taps[i][0], dst.taps[i][1], dst.taps[i][2] = dt, dy, dx
+    d.n_chain = len(pb.chains)
+    for i, c in enumerate(pb.chains):
+        fill(d.chain[i], c)
+    d.has_res_proj = int(pb.res is not None)
+    if pb.res is not None:
+        fill(d.res, pb.res)
+    for i, v in enumerate(pb.piece_col):
+        d.piece_col[i] = v
+    n_img = B * T
+    assert hid_bias.shape == (n_img, 128) and img_bias.shape == (n_img, 64) and hid_bias.is_contiguous() and img_bias.is_contiguous()
+    assert (res_bias is None) == (pb.res is None)
+    scratch, nbytes = None, 0
+    if col_sums is not None:
+        assert col_sums.shape == (n_img, 64) and col_sums.dtype == torch.float32 and col_sums.is_contiguous()
+        nbytes = _lib.lib().stp3_block_fused_scratch_bytes(n_img)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.hi.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.hi.device):
+        code = _lib.lib().stp3_block_fused_fwd(
+            ctypes.byref(d), mid.hi.data_ptr(), mid.lo.data_ptr(), x.hi.data_ptr(), x.lo.data_ptr(), pb.w.data_ptr(),
+            hid_bias.data_ptr(), img_bias.data_ptr(), ptr(res_bias), out.hi.data_ptr(), out.lo.data_ptr(), ptr(col_sums),
+            ptr(scratch), nbytes, torch.cuda.current_stream(x.hi.device).cuda_stream)
+    _lib.check(code, "stp3_block_fused_fwd")
+    return out
+
+
 def bias_table(pc: PackedConv, n_img: int) -> torch.Tensor:
     """(n_img, bn) per-image bias initialised with the convolution's own bias; the spatially constant branches are
     accumulated on top (pool_bias / small_linear with accumulate=True)."""

@@ -10,6 +10,7 @@ TemporalBlock data flow on the device (channels-last hi/lo planes, o = half roun
 Spatially constant input channels (the broadcast ego-motion of stp3.py:145-152) are never materialised: they enter
 every 1x1x1 convolution that reads x as a per-image bias.
 """
+import os
 from collections import OrderedDict
 from typing import Optional
 
@@ -177,6 +178,30 @@ class TemporalBlock(PackedModule):
             P["a2p"] = dense.pack_conv(wm[:, :cs].reshape(128, cs, 1, 1).contiguous(), torch.cat([b2p, bjp]), bn=128)
             if nc:
                 P["a2p_c"] = wm[:, cs:].contiguous()
+        # ---- the block's tail as ONE back-to-back kernel (stp3_block_fused_fwd): paths + aggregation + residual
+        n16 = (half + 15) // 16 * 16
+        if (os.environ.get("STP3_BLOCK_FUSED", "0") != "0" and cout <= 64 and cs <= 64 and hp == 64 and 3 * o <= 128 and
+                3 * n16 <= 144 and (not shared or 2 * o == 64)):
+            w2r = flat(w2)[:, :cs].reshape(half, cs, 1, 1, 1)
+            if shared:       # both mid paths in one K block: one block-diagonal chain, then path 2
+                chains = [(0, 0, wbc, 0, 64, 0), (1, 0, w2r, 0, n16, 64)]
+                piece_col = [8 * pp for pp in range(8)] + [64 + 8 * q for q in range(o // 8)]
+            else:
+                chains = [(0, 0, wt, 0, n16, 0), (0, 64, ws, 0, n16, n16), (1, 0, w2r, 0, n16, 2 * n16)]
+                piece_col = [n16 * k + 8 * q for k in range(3) for q in range(o // 8)]
+            piece_col += [-1] * (16 - len(piece_col))
+            agg_w = torch.zeros(64, 128, device=w0.device)
+            hid_b = torch.zeros(128, device=w0.device)
+            for k, bk in enumerate((bt, bs, b2)):
+                agg_w[:cout, k * o:k * o + half] = wg[:, k * half:(k + 1) * half]
+                hid_b[k * o:k * o + half] = bk
+            P["tail"] = dense.pack_block_tail(chains, agg_w, flat(wj)[:, :cs] if self.projection is not None else None,
+                                              piece_col)
+            P["tail_hid_bias"] = hid_b
+            if nc:           # path 2 reads the spatially constant channels too: they shift its hidden bias per image
+                wc = torch.zeros(128, nc, device=w0.device)
+                wc[2 * o:2 * o + half] = flat(w2)[:, cs:]
+                P["tail_hid_c"] = wc
         return P
 
     def forward_hl(self, x: dense.HL, const: Optional[torch.Tensor] = None,
@@ -201,6 +226,8 @@ class TemporalBlock(PackedModule):
             dense.small_linear(const, wc, b, False, bias=pc.bias)
             return b
 
+        if "tail" in P:
+            return self._forward_fused(x, const, sums, out_sums, P, const_bias)
         m1 = P["m1"]
         ap = P["ap"]
         agg = dense.HL.empty(B, T, H, W, 3 * o, dev, cp=ap)
@@ -244,6 +271,50 @@ class TemporalBlock(PackedModule):
                 assert nc == 0, "an identity skip cannot carry spatially constant extra channels"
                 res = x
         return dense.conv(agg, P["agg"], relu=True, img_bias=pbias, residual=res, res_after_act=True, col_sums=out_sums)
+
+    def _forward_fused(self, x, const, sums, out_sums, P, const_bias):
+        """Entry convolutions of paths 0 / 1 as one launch, then the whole tail of the block (both spatio-temporal
+        convolutions, path 2, aggregation, pyramid-pooling bias, projection / identity residual, output column sums) in
+        the back-to-back kernel: the concat tensor and the separate path-2 / projection passes over x disappear."""
+        B, T, H, W, _ = x.hi.shape
+        dev = x.hi.device
+        n_img = B * T
+        nc = 0 if const is None else const.shape[1]
+        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
+        if nc:
+            hid = torch.empty((n_img, 128), dtype=torch.float32, device=dev)
+            dense.small_linear(const, P["tail_hid_c"], hid, False, bias=P["tail_hid_bias"])
+        else:
+            key = ("tail_hid", n_img)
+            if key not in P:
+                P[key] = P["tail_hid_bias"].unsqueeze(0).expand(n_img, -1).contiguous()
+            hid = P[key]
+        if self.use_pyramid_pooling:
+            ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
+            assert (ph, pw) == (H, W), "pyramid pooling must span the whole map (as configured by TemporalModel)"
+            if sums is None:
+                sums = dense.spatial_sum(x)
+            pbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev)
+            dense.pool_bias(sums, T, self.in_channels, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
+                            const=const if nc else None, bias=P["agg"].bias)
+        else:
+            key = ("tail_agg_bias", n_img)
+            if key not in P:
+                P[key] = P["agg"].bias.unsqueeze(0).expand(n_img, -1).contiguous()
+            pbias = P[key]
+        rbias = None
+        if self.projection is not None:
+            if nc:
+                rbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev)
+                dense.small_linear(const, P["proj_c"], rbias, False, bias=P["proj"].bias)
+            else:
+                key = ("tail_res_bias", n_img)
+                if key not in P:
+                    P[key] = P["proj"].bias.unsqueeze(0).expand(n_img, -1).contiguous()
+                rbias = P[key]
+        y = dense.block_tail(mid, x, P["tail"], hid, pbias, rbias, col_sums=out_sums)
+        y.c = self.out_channels
+        return y
 
     def forward(self, *inputs):
         """x (B, C, T, H, W) fp32 -> (B, Cout, T, H, W) fp32, like the reference module."""

@@ -233,3 +233,30 @@ def test_aspp_fused_kernel_vs_oracle(B, H, W, monkeypatch):
         assert "fused" not in head2.packed()
         assert (y - y2).abs().max() <= 2e-5 * y2.abs().max(), "fused and unfused ASPP disagree"
     print(f"aspp fused {B}x{H}x{W}: {err:.2e} of max vs fp64 oracle")
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 24, 40), (2, 50, 36), (1, 200, 200)])
+def test_temporal_block_fused_tail_vs_oracle(B, H, W, monkeypatch):
+    """TemporalModel(70 -> 64, S = 3) with each block's tail (spatio-temporal convolutions of both paths, path 2, aggregation,
+    pyramid-pooling bias, projection / identity residual, output sums) in the back-to-back kernel stp3_block_fused_fwd:
+    block 1 = three chains of 35 channels + projection + ego-motion channels as per-image biases, block 2 = block-diagonal
+    chain + identity residual.  Against the fp64 oracle on the materialised 70-channel input and against the unfused
+    launch sequence, incl. ragged tiles and the frame-0 causal padding."""
+    x = dense_input((B, 3, 70, H, W), 41)
+    x[:, :, 64:] = x[:, :, 64:, :1, :1]                        # the six ego-motion channels are spatially constant
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("STP3_BLOCK_FUSED", fused)
+        with torch.no_grad():
+            tm = TD.init_exact(TemporalModel(70, 3, (H, W), start_out_channels=64), seed=42).eval()
+            if fused == "1":
+                ref = TD.temporal_model(x.double(), f64(tm))
+            tm = tm.to(DEV)
+            tm.model[0].n_const = 6
+            const = x[:, :, 64:, 0, 0].reshape(B * 3, 6).contiguous().to(DEV)
+            y = dense.to_f32(tm.forward_hl(dense.from_f32(x[:, :, :64].to(DEV)), const=const), 0, 64)
+            assert ("tail" in tm.model[0].packed()) == (fused == "1") and ("tail" in tm.model[1].packed()) == (fused == "1")
+        outs[fused] = y
+        err = close(y, ref)
+        print(f"temporal model {B}x{H}x{W} fused={fused}: {err:.2e} of max vs fp64 oracle")
+    assert (outs["1"] - outs["0"]).abs().max() <= 5e-5 * outs["0"].abs().max(), "fused and unfused block tails disagree"
