@@ -26,7 +26,7 @@ namespace stp3 {
 
 constexpr int kBlkThreads = 320;
 constexpr int kBlkMaxChains = 3;
-constexpr int kBlkMaxTaps = 18 + 9 + 1;
+constexpr int kBlkMaxTaps = 32;                 // 18 + 9 + 1 path taps + the projection's
 constexpr int kBlkNA = 3, kBlkNB = 3;
 constexpr int kBlkAStage = 2 * 8 * 16 * 128;
 constexpr int kBlkBStage = 2 * 64 * 128;
