@@ -7,6 +7,7 @@
 // writes the three paths into a 128-channel concat tensor and reads it back (2 x 246 MB per block and 4-sample step) and
 // needs one more pass over x for path 2 / the projection.  Here a CTA pair keeps a 16x16-pixel tile on chip:
 //
+//   (taps of one kernel column share ONE activation load: the box holds 8 + 2 image rows, tap j reads it shifted by j rows)
 //   main(u) : up to three MMA chains accumulate the paths side by side into ONE TMEM accumulator (chain c at column
 //             offset 48*c / 64: the concat happens in TMEM), each chain with its own input tensor, tap list, MMA width N
 //             and K-step range
@@ -27,8 +28,10 @@ namespace stp3 {
 constexpr int kBlkThreads = 320;
 constexpr int kBlkMaxChains = 3;
 constexpr int kBlkMaxTaps = 32;                 // 18 + 9 + 1 path taps + the projection's
-constexpr int kBlkNA = 3, kBlkNB = 3;
-constexpr int kBlkAStage = 2 * 8 * 16 * 128;
+constexpr int kBlkNA = 2, kBlkNB = 3;
+constexpr int kBlkBoxRows = 10;                   // 8 image rows + 2: one activation load serves the three dy taps of a kernel column
+constexpr int kBlkAStage = 2 * kBlkBoxRows * 16 * 128;
+constexpr int kBlkMaxGroups = 16;
 constexpr int kBlkBStage = 2 * 64 * 128;
 constexpr int kBlkPPlane = 128 * 128;
 constexpr int kAcc1Stride = 160;                  // TMEM columns between the two hidden accumulators (144 used)
@@ -38,6 +41,7 @@ struct BlkChain {
   int src;                  // 0 = mid tensor, 1 = x tensor
   int cin_off;              // first channel of the 64-channel K block read from the source
   int tap0, ntaps;
+  int grp0, ngrp;           // tap groups: runs of <= 3 taps with the same (dt, dx) and consecutive dy share one activation load
   int n_mma;                // MMA width (multiple of 16)
   int tmem_col;             // column offset inside the hidden accumulator
   int ks_first, ks_end;     // UMMA_K = 16 steps that carry data
@@ -52,6 +56,7 @@ struct BlkParams {
   int has_res_proj;         // acc3 = x . W_projection
   BlkChain res;
   signed char tap[kBlkMaxTaps][4];        // (dt, dy, dx)
+  unsigned char gstart[kBlkMaxGroups], gsize[kBlkMaxGroups];   // first tap / number of taps of every group
   int piece_col[16];        // TMEM column (inside the hidden accumulator) of the 8-channel piece pp of P, -1 = zeros
   const float* hid_bias;    // [n_img][128] bias of the hidden channels in P order
   const float* img_bias;    // [n_img][64]  aggregation bias (+ pyramid-pooling branch)
@@ -66,10 +71,12 @@ struct BlkParams {
   int wagg_blk0;            // two weight blocks (K blocks of P) of the aggregation conv
 };
 
-__device__ __forceinline__ bool blk_tap_is_padding(const BlkParams& p, int t, int tidx, int oy_tile, int ox0) {
-  const int tt = tidx + p.tap[t][0];
-  const int ylo = oy_tile + p.tap[t][1], yhi = oy_tile + 15 + p.tap[t][1];
-  const int xlo = ox0 + p.tap[t][2], xhi = ox0 + 15 + p.tap[t][2];
+// true if every input element the tap group touches for this (whole, 16x16) tile is zero padding
+__device__ __forceinline__ bool blk_group_is_padding(const BlkParams& p, int g, int tidx, int oy_tile, int ox0) {
+  const int t0 = p.gstart[g];
+  const int tt = tidx + p.tap[t0][0];
+  const int ylo = oy_tile + p.tap[t0][1], yhi = oy_tile + 15 + p.tap[t0][1] + p.gsize[g] - 1;
+  const int xlo = ox0 + p.tap[t0][2], xhi = ox0 + 15 + p.tap[t0][2];
   return tt < 0 || tt >= p.T || yhi < 0 || ylo >= p.H || xhi < 0 || xlo >= p.W;
 }
 
@@ -165,10 +172,11 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
       const int bidx = img / p.T, tidx = img % p.T;
       for (int c = 0; c < p.n_chain; ++c) {
         const BlkChain& ch = p.chain[c];
-        for (int t = ch.tap0; t < ch.tap0 + ch.ntaps; ++t) {
-          if (blk_tap_is_padding(p, t, tidx, oy_tile, ox0)) continue;
-          load_a(ch.src, ch.cin_off, ox0 + p.tap[t][2], oy0 + p.tap[t][1], tidx + p.tap[t][0], bidx);
-          load_b(ch.wblk0 + (t - ch.tap0));
+        for (int g = ch.grp0; g < ch.grp0 + ch.ngrp; ++g) {
+          if (blk_group_is_padding(p, g, tidx, oy_tile, ox0)) continue;
+          const int t0 = p.gstart[g];
+          load_a(ch.src, ch.cin_off, ox0 + p.tap[t0][2], oy0 + p.tap[t0][1], tidx + p.tap[t0][0], bidx);
+          for (int j = 0; j < p.gsize[g]; ++j) load_b(ch.wblk0 + (t0 + j - ch.tap0));
         }
       }
       if (pend) proj_loads();
@@ -242,22 +250,27 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf1 * kAcc1Stride + ch.tmem_col);
         const uint32_t idesc = ptx::umma_idesc_bf16(256, ch.n_mma);
         uint32_t accumulate = 0;
-        for (int t = ch.tap0; t < ch.tap0 + ch.ntaps; ++t) {
-          if (blk_tap_is_padding(p, t, tidx, oy_tile, ox0)) continue;
+        for (int g = ch.grp0; g < ch.grp0 + ch.ngrp; ++g) {
+          if (blk_group_is_padding(p, g, tidx, oy_tile, ox0)) continue;
           ptx::mbar_wait(&a_full[as], aph);
-          ptx::mbar_wait(&b_full[bs], bph);
           ptx::tc_fence_after();
-          if (ptx::elect_one_sync()) {
-            const uint32_t a_hi = ptx::smem_u32(a_ring + (size_t)as * kBlkAStage);
-            const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBlkBStage);
-            issue(tmem_d, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + 64 * 128, idesc, ch.ks_first, ch.ks_end, accumulate);
-            ptx::umma_commit_pair(&b_empty[bs]);
-            ptx::umma_commit_pair(&a_empty[as]);
+          const uint32_t a_hi0 = ptx::smem_u32(a_ring + (size_t)as * kBlkAStage);
+          for (int j = 0; j < p.gsize[g]; ++j) {
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one_sync()) {
+              const uint32_t a_hi = a_hi0 + (uint32_t)(j * 16 * 128);          // tap j of the group: shifted by j image rows
+              const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBlkBStage);
+              issue(tmem_d, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + 64 * 128, idesc, ch.ks_first, ch.ks_end, accumulate);
+              ptx::umma_commit_pair(&b_empty[bs]);
+            }
+            __syncwarp();
+            accumulate = 1;
+            if (++bs == kBlkNB) { bs = 0; bph ^= 1; }
           }
+          if (ptx::elect_one_sync()) ptx::umma_commit_pair(&a_empty[as]);
           __syncwarp();
-          accumulate = 1;
           if (++as == kBlkNA) { as = 0; aph ^= 1; }
-          if (++bs == kBlkNB) { bs = 0; bph ^= 1; }
         }
       }
       if (ptx::elect_one_sync()) ptx::umma_commit_pair(&acc1_full[buf1]);
@@ -478,7 +491,7 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   STP3_CHECK_ARG(nt < (1ll << 31), "grid too large");
   p.n_tiles = (int)nt;
   p.n_chain = d->n_chain;
-  int t = 0, blk = 0;
+  int t = 0, blk = 0, n_grp = 0;
   auto fill = [&](BlkChain& c, const stp3_block_chain& s) -> int {
     c.src = s.src; c.cin_off = s.cin_off; c.tap0 = t; c.ntaps = s.n_taps; c.n_mma = s.n_mma; c.tmem_col = s.tmem_col;
     c.ks_first = s.k_lo / 16; c.ks_end = s.k_hi / 16; c.wblk0 = blk;
@@ -493,6 +506,18 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
       centre |= s.taps[i][0] == 0 && s.taps[i][1] == 0 && s.taps[i][2] == 0;
     }
     if (!centre) return set_error(STP3_EINVAL, "every chain needs its centre tap");
+    // tap groups: consecutive taps with the same (dt, dx) and dy advancing by one
+    c.grp0 = n_grp;
+    for (int i = c.tap0; i < c.tap0 + c.ntaps;) {
+      int g = 1;
+      while (g < 3 && i + g < c.tap0 + c.ntaps && p.tap[i + g][0] == p.tap[i][0] && p.tap[i + g][2] == p.tap[i][2] &&
+             p.tap[i + g][1] == p.tap[i][1] + g)
+        ++g;
+      if (n_grp >= kBlkMaxGroups) return set_error(STP3_EINVAL, "too many tap groups");
+      p.gstart[n_grp] = (unsigned char)i; p.gsize[n_grp] = (unsigned char)g; ++n_grp;
+      i += g;
+    }
+    c.ngrp = n_grp - c.grp0;
     blk += s.n_taps;
     return STP3_OK;
   };
@@ -523,7 +548,7 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
     const cuuint64_t dims[5] = {(cuuint64_t)cs, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->T, (cuuint64_t)d->B};
     const cuuint64_t strides[4] = {(cuuint64_t)cs * 2, (cuuint64_t)d->W * cs * 2, (cuuint64_t)d->H * d->W * cs * 2,
                                    (cuuint64_t)d->T * d->H * d->W * cs * 2};
-    const cuuint32_t box[5] = {64, 16, 8, 1, 1};
+    const cuuint32_t box[5] = {64, 16, (cuuint32_t)kBlkBoxRows, 1, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(planes[i]), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -180,7 +180,7 @@ class TemporalBlock(PackedModule):
                 P["a2p_c"] = wm[:, cs:].contiguous()
         # ---- the block's tail as ONE back-to-back kernel (stp3_block_fused_fwd): paths + aggregation + residual
         n16 = (half + 15) // 16 * 16
-        if (os.environ.get("STP3_BLOCK_FUSED", "0") != "0" and cout <= 64 and cs <= 64 and hp == 64 and 3 * o <= 128 and
+        if (os.environ.get("STP3_BLOCK_FUSED", "1") != "0" and cout <= 64 and cs <= 64 and hp == 64 and 3 * o <= 128 and
                 3 * n16 <= 144 and (not shared or 2 * o == 64)):
             w2r = flat(w2)[:, :cs].reshape(half, cs, 1, 1, 1)
             if shared:       # both mid paths in one K block: one block-diagonal chain, then path 2
