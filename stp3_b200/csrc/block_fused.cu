@@ -147,14 +147,19 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
       __syncwarp();
       if (++as == kBlkNA) { as = 0; aph ^= 1; }
     };
-    auto load_b = [&](int blk) {
+    // weight block `blk` = [hi 128 rows][lo 128 rows]; this CTA multiplies n_mma / 2 of its 64 rows: only those are fetched
+    // (boxes of 8 rows) -- with 28 taps per tile the weights, not the activations, were the larger L2 -> SM stream
+    auto load_b = [&](int blk, int n_mma) {
       ptx::mbar_wait(&b_empty[bs], bph ^ 1);
       if (ptx::elect_one_sync()) {
         const uint32_t bar = ptx::mapa(ptx::smem_u32(&b_full[bs]), 0);
         unsigned char* dst = b_ring + (size_t)bs * kBlkBStage;
-        ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)kBlkBStage);
-        ptx::tma_load_2d_pair(dst, &tm_w, bar, 0, blk * 256 + (int)rank * 64);
-        ptx::tma_load_2d_pair(dst + 64 * 128, &tm_w, bar, 0, blk * 256 + 128 + (int)rank * 64);
+        const int rows = n_mma / 2;
+        ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)(2 * rows * 128));
+        for (int r8 = 0; r8 < rows; r8 += 8) {
+          ptx::tma_load_2d_pair(dst + r8 * 128, &tm_w, bar, 0, blk * 256 + (int)rank * 64 + r8);
+          ptx::tma_load_2d_pair(dst + 64 * 128 + r8 * 128, &tm_w, bar, 0, blk * 256 + 128 + (int)rank * 64 + r8);
+        }
       }
       __syncwarp();
       if (++bs == kBlkNB) { bs = 0; bph ^= 1; }
@@ -162,8 +167,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
     int pend_x = 0, pend_y = 0, pend_t = 0, pend_b = 0;
     bool pend = false;
     auto proj_loads = [&]() {
-      load_b(p.wagg_blk0); load_b(p.wagg_blk0 + 1);
-      if (p.has_res_proj) { load_a(1, p.res.cin_off, pend_x, pend_y, pend_t, pend_b); load_b(p.res.wblk0); }
+      load_b(p.wagg_blk0, 64); load_b(p.wagg_blk0 + 1, 64);
+      if (p.has_res_proj) { load_a(1, p.res.cin_off, pend_x, pend_y, pend_t, pend_b); load_b(p.res.wblk0, 64); }
     };
     for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
       const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
@@ -176,7 +181,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
           if (blk_group_is_padding(p, g, tidx, oy_tile, ox0)) continue;
           const int t0 = p.gstart[g];
           load_a(ch.src, ch.cin_off, ox0 + p.tap[t0][2], oy0 + p.tap[t0][1], tidx + p.tap[t0][0], bidx);
-          for (int j = 0; j < p.gsize[g]; ++j) load_b(ch.wblk0 + (t0 + j - ch.tap0));
+          for (int j = 0; j < p.gsize[g]; ++j) load_b(ch.wblk0 + (t0 + j - ch.tap0), ch.n_mma);
         }
       }
       if (pend) proj_loads();
@@ -558,7 +563,7 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   {
     const cuuint64_t wd[2] = {64, (cuuint64_t)blk * 256};
     const cuuint64_t ws[1] = {128};
-    const cuuint32_t wb[2] = {64, 64};
+    const cuuint32_t wb[2] = {64, 8};
     const cuuint32_t we[2] = {1, 1};
     CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), wd, ws, wb, we,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
