@@ -697,7 +697,22 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
                 ops.bev_discount(pf.buf.view(1, S, X, Y, C), float(model.discount))
             for _ in range(2):
                 lift_nccl(); lift_peer()
-            peer = {"ms": ms_peer, "parity_vs_unsharded": parallel.max_over_ranks(err_p, dev) <= 1e-4,
+            # both as ONE CUDA graph (what a latency-critical deployment would run): unsharded vs frame-sharded + peer stores
+            graphed = None
+            try:
+                from stp3_b200.models.stp3 import GraphedPerception
+                g_full = GraphedPerception(model, 1, cfg.n_cameras, dev, entry="lift")
+                g_shard = GraphedPerception(model, 1, cfg.n_cameras, dev, entry="sharded")
+                for g in (g_full, g_shard):
+                    g(a[0], a[1], a[2], a[3], a[4])
+                torch.cuda.synchronize()
+                err_g = max(float((g_shard.out[k] - g_full.out[k]).abs().max() / g_full.out[k].abs().max())
+                            for k in ("segmentation", "pedestrian", "hdmap"))
+                graphed = {"ms_unsharded": timed(g_full.graph.replay), "ms_frame_sharded_peer_stores": timed(g_shard.graph.replay),
+                           "parity_vs_unsharded": parallel.max_over_ranks(err_g, dev) <= 1e-4}
+            except Exception as e:
+                graphed = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            peer = {"ms": ms_peer, "graphed": graphed, "parity_vs_unsharded": parallel.max_over_ranks(err_p, dev) <= 1e-4,
                     "lift_stage_ms_nccl_allgather": timed(lift_nccl), "lift_stage_ms_peer_stores": timed(lift_peer),
                     "how": "finalize epilogue stores each frame into every rank's symmetric-memory buffer (st.global on peer "
                            "addresses), two device-side barriers, no collective launch"}

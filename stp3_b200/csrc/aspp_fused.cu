@@ -422,7 +422,11 @@ extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, co
   }
   const size_t smem_bytes = 1024 + (size_t)kAsppNA * kAStage + (size_t)kAsppNB * kBStage + 4 * (size_t)kPPlane +
                             (kAsppMaxBranches * kAsppHidden + 8 * 64) * sizeof(float) + 32 * 8 + 16;
-  STP3_CUDA_OK(cudaFuncSetAttribute(aspp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  static thread_local int attr_dev = -1, occ_val = 0;           // once per device: these calls cost microseconds per eager launch
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const bool first_call = attr_dev != cur_dev;
+  if (first_call) STP3_CUDA_OK(cudaFuncSetAttribute(aspp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int num_sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -434,8 +438,11 @@ extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, co
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  int max_clusters = 0;
-  STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, aspp_fused_kernel, &cfg));
+  int max_clusters = occ_val;
+  if (first_call) {
+    STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, aspp_fused_kernel, &cfg));
+    occ_val = max_clusters; attr_dev = cur_dev;
+  }
   if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");
   if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

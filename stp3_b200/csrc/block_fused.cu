@@ -572,7 +572,11 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   }
   const size_t smem_bytes = 1024 + (size_t)kBlkNA * kBlkAStage + (size_t)kBlkNB * kBlkBStage + 4 * (size_t)kBlkPPlane +
                             2 * 8 * 64 * sizeof(float) + 32 * 8 + 16;
-  STP3_CUDA_OK(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  static thread_local int attr_dev = -1, occ_val = 0;           // once per device: these calls cost microseconds per eager launch
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const bool first_call = attr_dev != cur_dev;
+  if (first_call) STP3_CUDA_OK(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const int num_sms = blk_num_sms();
   cudaLaunchConfig_t cfg = {};
   unsigned pairs = (unsigned)(nt < num_sms / 2 ? nt : num_sms / 2);
@@ -582,8 +586,11 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  int max_clusters = 0;
-  STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, block_fused_kernel, &cfg));
+  int max_clusters = occ_val;
+  if (first_call) {
+    STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, block_fused_kernel, &cfg));
+    occ_val = max_clusters; attr_dev = cur_dev;
+  }
   if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");
   if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;
   p.sum_part = nullptr;

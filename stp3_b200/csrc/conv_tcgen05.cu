@@ -905,7 +905,13 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       p.na_stages = na; p.nb_stages = nb; p.b_resident = res ? 1 : 0;                                             \
       const size_t smem_bytes = 1024 + na * a_stage + (res ? wbytes : (size_t)nb * (size_t)p.b_tile_bytes) + SM::tail_bytes(); \
       auto kern = conv_igemm_kernel<BN_, PAIR_, STACK_>;                                                          \
-      STP3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));       \
+      /* once per kernel instantiation and device: the attribute call costs microseconds on every eager launch */ \
+      static thread_local int attr_dev = -1;                                                                      \
+      int cur_dev = 0; cudaGetDevice(&cur_dev);                                                                   \
+      if (attr_dev != cur_dev) {                                                                                  \
+        STP3_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));     \
+        attr_dev = cur_dev;                                                                                       \
+      }                                                                                                           \
       cudaLaunchConfig_t cfg = {};                                                                                \
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads);                                                \
       cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;                                                     \
@@ -915,8 +921,13 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       cfg.attrs = attr; cfg.numAttrs = PAIR_ ? 1 : 0;                                                             \
       if (PAIR_) {                                                                                                \
         /* co-resident pairs the device can host with this much shared memory (GPCs with an odd SM count) */      \
-        int max_clusters = 0;                                                                                     \
-        STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));                                  \
+        /* depends on the kernel and its shared-memory size only: cached per (device, smem size) */               \
+        static thread_local int occ_dev = -1, occ_val = 0; static thread_local size_t occ_smem = 0;               \
+        int max_clusters = occ_val;                                                                               \
+        if (occ_dev != cur_dev || occ_smem != smem_bytes) {                                                       \
+          STP3_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));                                \
+          occ_dev = cur_dev; occ_smem = smem_bytes; occ_val = max_clusters;                                       \
+        }                                                                                                         \
         if (max_clusters < 1) return set_error(STP3_EUNSUPPORTED, "no CTA pair fits on this device");             \
         if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;             \
       }                                                                                                           \

@@ -211,13 +211,21 @@ class STP3(nn.Module):
         gather = "nccl": ncclAllGather of the frames; gather = "peer": the finalize kernel's epilogue stores every frame
         into all ranks' buffers over NVLink itself (symmetric memory, parallel.PeerFrameBuffer) -- compute and collective in
         one kernel, bracketed by two device-side barriers."""
-        from .. import parallel
         S = self.receptive_field
         dev = feat.device
         h = {k: v.to(dev) for k, v in self.prepare_inputs(intrinsics, extrinsics, future_egomotion).items()}
         feat = feat[:, :S].contiguous()
         depth_logits = depth_logits[:, :S].contiguous() if depth_logits is not None else None
-        B = feat.shape[0]
+        return self.forward_device_frame_sharded(feat, depth_logits, **h, gather=gather)
+
+    def forward_device_frame_sharded(self, feat, depth_logits, cam_M, cam_t, ego_R, ego_t, const, gather="peer"):
+        """Device-only part of the frame-sharded forward (no host synchronisation): with gather="peer" the whole step --
+        splat of this rank's frames with the all-gather in the finalize epilogue, the two device-side barriers, discount,
+        temporal model, decoder -- can be captured in ONE CUDA graph (GraphedPerception(entry="sharded"))."""
+        from .. import parallel
+        h = {"cam_M": cam_M, "cam_t": cam_t, "ego_R": ego_R, "ego_t": ego_t, "const": const}
+        dev = feat.device
+        B, S = feat.shape[:2]
         X, Y = self.bev_size
         C = self.encoder_out_channels
         off, res, dim = self._bev_host()
@@ -288,7 +296,8 @@ class GraphedPerception:
 
     def __init__(self, model: STP3, batch: int, n_cameras: int, device=None, entry: str = "lift"):
         """entry "lift": the step enters at the encoder outputs (feat, depth_logits), STP3.forward_features;
-        entry "heads": at the trunk endpoints (r_lo, r_hi), STP3.forward_trunk_features (encoder heads included)."""
+        entry "heads": at the trunk endpoints (r_lo, r_hi), STP3.forward_trunk_features (encoder heads included);
+        entry "sharded": like "lift" but frame-sharded over the ranks of the default process group (latency mode)."""
         self.model = model
         self.entry = entry
         dev = torch.device(device) if device is not None else next(model.parameters()).device
@@ -296,11 +305,13 @@ class GraphedPerception:
         Hf, Wf = model.frustum.shape[1:3]
         N = n_cameras
         f32 = dict(dtype=torch.float32, device=dev)
-        if entry == "lift":
+        if entry in ("lift", "sharded"):
             self.big = ("feat", "depth_logits")
             first = {"feat": torch.zeros((batch, S, N, C, Hf, Wf), **f32),
                      "depth_logits": torch.zeros((batch, S, N, D, Hf, Wf), **f32)}
-            self._fwd = model.forward_device
+            # "sharded": the frame-sharded latency mode (all ranks capture and replay in lock-step; the exchange of the BEV
+            # frames is the finalize kernel's peer stores, so the graph holds no NCCL node)
+            self._fwd = model.forward_device if entry == "lift" else model.forward_device_frame_sharded
         elif entry == "heads":
             enc = model.encoder
             idx = {8: 3, 16: 4}[enc.downsample]
