@@ -470,9 +470,7 @@ def main():
         """End-to-end throughput with the copies of neighbouring steps overlapped with compute (PipelinedPerception):
         every step still moves its inputs host->device and its results device->host inside the timed region."""
         args_h = (host["feat"], host["depth_logits"], host["intrinsics"], host["extrinsics"], host["future_egomotion"])
-        # no explicit L2 flush here: every step's inputs arrive from the host and a step streams > 3 GB of activations
-        # through the 126 MB L2 (a flush kernel inside this continuously timed region would be timed as work)
-        pipe.between_steps = None
+        pipe.between_steps = flush.zero_            # L2 eviction between steps, on the compute stream
         for _ in range(3):
             pipe.submit(*args_h); pipe.collect()
         barrier()
@@ -510,8 +508,7 @@ def main():
         with torch.no_grad():
             pipe = PipelinedPerception(model, b, cfg.n_cameras, depth=2, device=dev, entry="heads" if heads else "lift")
         e2e_ms = timed_pipelined(pipe, K)
-        e2e_mode = ("pipelined (depth 2): copies of steps i-1 / i+1 overlap the CUDA graph of step i; inputs come from the host "
-                    "every step (no L2 flush kernel inside the continuously timed region)")
+        e2e_mode = "pipelined (depth 2): copies of steps i-1 / i+1 overlap the CUDA graph of step i"
     else:
         for _ in range(2):
             step_e2e()

@@ -435,40 +435,6 @@ def bias_table(pc: PackedConv, n_img: int) -> torch.Tensor:
     return pc.bias.unsqueeze(0).expand(n_img, -1).contiguous()
 
 
-# ------------------------------------------------------------------------------------------------ side stream
-_SIDE = {}
-
-
-class overlapped:
-    """Context: the small kernels launched inside run on a per-device side stream, concurrently with whatever the caller
-    launches on the current stream afterwards, until `join()`.  Used for the bias-table helpers (pool_bias, small_linear:
-    a few blocks of 256 threads, no shared memory to speak of) that sit between two convolutions of a dependency chain
-    without depending on the first one; inside a CUDA-graph capture the fork / join become parallel graph branches.
-    Tensors the side kernels write must be allocated BEFORE entering (on the current stream)."""
-
-    def __init__(self, device):
-        self.dev = torch.device(device)
-        self.cur = torch.cuda.current_stream(self.dev)
-        key = (self.dev.index, torch.cuda.is_current_stream_capturing())
-        if key not in _SIDE:
-            _SIDE[key] = torch.cuda.Stream(device=self.dev)
-        self.side = _SIDE[key]
-        self.ctx = None
-
-    def __enter__(self):
-        self.side.wait_stream(self.cur)
-        self.ctx = torch.cuda.stream(self.side)
-        self.ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        self.ctx.__exit__(*exc)
-        return False
-
-    def join(self):
-        self.cur.wait_stream(self.side)
-
-
 # ------------------------------------------------------------------------------------------------ aux kernels
 def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream

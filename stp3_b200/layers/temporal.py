@@ -280,42 +280,38 @@ class TemporalBlock(PackedModule):
         dev = x.hi.device
         n_img = B * T
         nc = 0 if const is None else const.shape[1]
-        a1_bias = const_bias(P.get("a1_c"), P["a1"])
-        # bias tables of the tail kernel: small helper kernels that do not depend on the entry convolution -- they run on
-        # a side stream underneath it
-        hid = torch.empty((n_img, 128), dtype=torch.float32, device=dev) if nc else None
-        pbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev) if self.use_pyramid_pooling else None
-        rbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev) if (self.projection is not None and nc) else None
-        if self.use_pyramid_pooling and sums is None:
-            sums = dense.spatial_sum(x)
-        ov = dense.overlapped(dev)
-        with ov:
-            if nc:
-                dense.small_linear(const, P["tail_hid_c"], hid, False, bias=P["tail_hid_bias"])
-            if self.use_pyramid_pooling:
-                ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
-                assert (ph, pw) == (H, W), "pyramid pooling must span the whole map (as configured by TemporalModel)"
-                dense.pool_bias(sums, T, self.in_channels, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
-                                const=const if nc else None, bias=P["agg"].bias)
-            if rbias is not None:
-                dense.small_linear(const, P["proj_c"], rbias, False, bias=P["proj"].bias)
-        mid = dense.conv(x, P["a1"], relu=True, img_bias=a1_bias)
-        ov.join()
-        if hid is None:
+        mid = dense.conv(x, P["a1"], relu=True, img_bias=const_bias(P.get("a1_c"), P["a1"]))
+        if nc:
+            hid = torch.empty((n_img, 128), dtype=torch.float32, device=dev)
+            dense.small_linear(const, P["tail_hid_c"], hid, False, bias=P["tail_hid_bias"])
+        else:
             key = ("tail_hid", n_img)
             if key not in P:
                 P[key] = P["tail_hid_bias"].unsqueeze(0).expand(n_img, -1).contiguous()
             hid = P[key]
-        if pbias is None:
+        if self.use_pyramid_pooling:
+            ph, pw = self.pyramid_pooling.pool_sizes[0][1:]
+            assert (ph, pw) == (H, W), "pyramid pooling must span the whole map (as configured by TemporalModel)"
+            if sums is None:
+                sums = dense.spatial_sum(x)
+            pbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev)
+            dense.pool_bias(sums, T, self.in_channels, H * W, True, P["pool_w1"], P["pool_b1"], P["pool_w2"], pbias, False,
+                            const=const if nc else None, bias=P["agg"].bias)
+        else:
             key = ("tail_agg_bias", n_img)
             if key not in P:
                 P[key] = P["agg"].bias.unsqueeze(0).expand(n_img, -1).contiguous()
             pbias = P[key]
-        if self.projection is not None and rbias is None:
-            key = ("tail_res_bias", n_img)
-            if key not in P:
-                P[key] = P["proj"].bias.unsqueeze(0).expand(n_img, -1).contiguous()
-            rbias = P[key]
+        rbias = None
+        if self.projection is not None:
+            if nc:
+                rbias = torch.empty((n_img, 64), dtype=torch.float32, device=dev)
+                dense.small_linear(const, P["proj_c"], rbias, False, bias=P["proj"].bias)
+            else:
+                key = ("tail_res_bias", n_img)
+                if key not in P:
+                    P[key] = P["proj"].bias.unsqueeze(0).expand(n_img, -1).contiguous()
+                rbias = P[key]
         y = dense.block_tail(mid, x, P["tail"], hid, pbias, rbias, col_sums=out_sums)
         y.c = self.out_channels
         return y

@@ -112,20 +112,9 @@ class Decoder(PackedModule):
                 "members": members, "mask": mask}
 
     def _basic_block(self, x, P, key, has_ds):
-        if not has_ds:
-            y = dense.conv(x, P[f"{key}.c1"], relu=True)
-            return dense.conv(y, P[f"{key}.c2"], relu=True, residual=x)     # relu(bn2(conv2) + identity)
-        # the 1x1 stride-2 downsample of the skip and conv1 both read x and are independent: the small downsample launch
-        # runs on a side stream next to conv1 (whose grid does not fill the GPU at these map sizes)
-        pds = P[f"{key}.ds"]
-        B, T, H, W, _ = x.hi.shape
-        res = dense.HL.empty(B, T, (H + 1) // 2, (W + 1) // 2, pds.cout, x.hi.device, cp=pds.bn)
-        ov = dense.overlapped(x.hi.device)
-        with ov:
-            dense.conv(x, pds, out=res)
         y = dense.conv(x, P[f"{key}.c1"], relu=True)
-        ov.join()
-        return dense.conv(y, P[f"{key}.c2"], relu=True, residual=res)
+        res = dense.conv(x, P[f"{key}.ds"]) if has_ds else x
+        return dense.conv(y, P[f"{key}.c2"], relu=True, residual=res)       # relu(bn2(conv2) + identity)
 
     def forward_hl(self, x: dense.HL):
         self._require_eval()
