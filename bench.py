@@ -554,7 +554,10 @@ def main():
     # latency mode (north_star): global batch 1 < #GPUs, camera frames sharded, ONE all-gather of raw BEV frames
     latency = None
     if world > 1 and perceive and not args.no_extras:
-        latency = time_latency_mode(model, cfg, dev, flush, rank, world)
+        try:
+            latency = time_latency_mode(model, cfg, dev, flush, rank, world)
+        except Exception as e:            # never let the extra mode cost the main line
+            latency = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         ms_per_step = total_ms / K
