@@ -28,11 +28,12 @@ namespace stp3 {
 constexpr int kBlkThreads = 320;
 constexpr int kBlkMaxChains = 3;
 constexpr int kBlkMaxTaps = 32;                 // 18 + 9 + 1 path taps + the projection's
-constexpr int kBlkNA = 2, kBlkNB = 3;
+constexpr int kBlkNA = 3, kBlkNB = 4;          // the kernel is TMA-latency bound: as many activation bytes in flight as fit
 constexpr int kBlkBoxRows = 10;                   // 8 image rows + 2: one activation load serves the three dy taps of a kernel column
 constexpr int kBlkAStage = 2 * kBlkBoxRows * 16 * 128;
 constexpr int kBlkMaxGroups = 16;
-constexpr int kBlkBStage = 2 * 64 * 128;
+constexpr int kBlkBRows = 32;                     // weight rows per CTA and plane: chains are at most 64 wide
+constexpr int kBlkBStage = 2 * kBlkBRows * 128;
 constexpr int kBlkPPlane = 128 * 128;
 constexpr int kAcc1Stride = 160;                  // TMEM columns between the two hidden accumulators (144 used)
 constexpr int kAcc2Col = 320, kAcc3Col = 384;
@@ -158,7 +159,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
         ptx::mbar_arrive_expect_tx_cluster(bar, (uint32_t)(2 * rows * 128));
         for (int r8 = 0; r8 < rows; r8 += 8) {
           ptx::tma_load_2d_pair(dst + r8 * 128, &tm_w, bar, 0, blk * 256 + (int)rank * 64 + r8);
-          ptx::tma_load_2d_pair(dst + 64 * 128 + r8 * 128, &tm_w, bar, 0, blk * 256 + 128 + (int)rank * 64 + r8);
+          ptx::tma_load_2d_pair(dst + kBlkBRows * 128 + r8 * 128, &tm_w, bar, 0, blk * 256 + 128 + (int)rank * 64 + r8);
         }
       }
       __syncwarp();
@@ -216,7 +217,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
         if (ptx::elect_one_sync()) {
           const uint32_t a_hi = ptx::smem_u32(p_buf + (size_t)kb2 * 2 * kBlkPPlane);
           const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBlkBStage);
-          issue(tmem_base + kAcc2Col, a_hi, a_hi + kBlkPPlane, b_hi, b_hi + 64 * 128, idesc64, 0, 4, kb2 > 0 ? 1u : 0u);
+          issue(tmem_base + kAcc2Col, a_hi, a_hi + kBlkPPlane, b_hi, b_hi + kBlkBRows * 128, idesc64, 0, 4, kb2 > 0 ? 1u : 0u);
           ptx::umma_commit_pair(&b_empty[bs]);
           ptx::umma_commit_pair(&p_empty[kb2]);
         }
@@ -231,7 +232,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
         if (ptx::elect_one_sync()) {
           const uint32_t a_hi = ptx::smem_u32(a_ring + (size_t)as * kBlkAStage);
           const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBlkBStage);
-          issue(tmem_base + kAcc3Col, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + 64 * 128, idesc64, p.res.ks_first, p.res.ks_end, 0u);
+          issue(tmem_base + kAcc3Col, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + kBlkBRows * 128, idesc64, p.res.ks_first, p.res.ks_end, 0u);
           ptx::umma_commit_pair(&b_empty[bs]);
           ptx::umma_commit_pair(&a_empty[as]);
         }
@@ -266,7 +267,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
             if (ptx::elect_one_sync()) {
               const uint32_t a_hi = a_hi0 + (uint32_t)(j * 16 * 128);          // tap j of the group: shifted by j image rows
               const uint32_t b_hi = ptx::smem_u32(b_ring + (size_t)bs * kBlkBStage);
-              issue(tmem_d, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + 64 * 128, idesc, ch.ks_first, ch.ks_end, accumulate);
+              issue(tmem_d, a_hi, a_hi + kBlkAStage / 2, b_hi, b_hi + kBlkBRows * 128, idesc, ch.ks_first, ch.ks_end, accumulate);
               ptx::umma_commit_pair(&b_empty[bs]);
             }
             __syncwarp();
