@@ -92,8 +92,8 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
   unsigned char* a_ring = smem;
   unsigned char* b_ring = a_ring + kBlkNA * kBlkAStage;
   unsigned char* p_buf = b_ring + kBlkNB * kBlkBStage;          // [kb2][hi | lo][128 rows x 128 B]
-  float* s_hb = reinterpret_cast<float*>(p_buf + 4 * kBlkPPlane);   // [8 warps][64] hidden-bias slices
-  float* s_wb = s_hb + 8 * 64;                                      // [8 warps][64] img_bias (32) | res_bias (32)
+  float* s_hb = reinterpret_cast<float*>(p_buf + 4 * kBlkPPlane);   // [4 converting warps][128] hidden bias of the image
+  float* s_wb = s_hb + 8 * 64;                                      // [4 finishing warps][128] img_bias (64) | res_bias (64)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + 8 * 64);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kBlkNA;
@@ -116,12 +116,12 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
     for (int i = 0; i < kBlkNB; ++i) { ptx::mbar_init(&b_full[i], 2); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc1_full[i], 1);
-      ptx::mbar_init(&acc1_empty[i], 16);
+      ptx::mbar_init(&acc1_empty[i], 8);          // the 4 converting warps of both CTAs
       ptx::mbar_init(&p_full[i], 8);
       ptx::mbar_init(&p_empty[i], 1);
     }
     ptx::mbar_init(acc2_full, 1);
-    ptx::mbar_init(acc2_empty, 16);
+    ptx::mbar_init(acc2_empty, 8);                // the 4 finishing warps of both CTAs
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_slot);
@@ -287,152 +287,154 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
     }
     if (pend) proj();
   } else if (warp >= 2) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: two independent warp groups =====================
+    // warps 2..5 CONVERT (hidden accumulator -> operand P), warps 6..9 FINISH (acc2 / acc3 -> output): the conversion of
+    // tile u+1 overlaps the output of tile u instead of queueing behind it in the same warps.  Each group has one warp per
+    // TMEM lane quarter (warp id % 4).
     const int e = warp - 2;
     const int q = warp & 3;
-    const int half = e >> 2;                       // K block of P this warp writes / 32-channel half of the output it stores
     const int r = q * 32 + lane;
-    int buf1 = 0; uint32_t acc1_ph = 0, pph = 0, t2ph = 0;
-    unsigned char* p_hi = p_buf + (size_t)half * 2 * kBlkPPlane + (size_t)r * 128;
-    unsigned char* p_lo = p_hi + kBlkPPlane;
-    const uint32_t sw = (uint32_t)(r & 7);
-    float* hb = s_hb + e * 64;
-    float* wb = s_wb + e * 64;
-    float sacc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
-    int sum_img = -1;
-    auto flush_sums = [&](int img_) {              // 32 lanes x 32 columns -> lane l holds column 32*half + l
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < off) {
-            const float send = upper ? sacc[i] : sacc[i + off];
-            const float keep = upper ? sacc[i + off] : sacc[i];
-            sacc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-      }
-      p.sum_part[(((size_t)blockIdx.x * 4 + q) * p.n_img + img_) * 64 + 32 * half + lane] = sacc[0];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
-    };
     ptx::griddep_wait();
-    for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
-      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int oy = (rem / p.tiles_x) * 16 + (int)rank * 8 + (r >> 4), ox = (rem % p.tiles_x) * 16 + (r & 15);
-      if (p.sum_part && img != sum_img) {          // tiles come in image order
-        if (sum_img >= 0) flush_sums(sum_img);
-        sum_img = img;
-      }
-      {                                            // this warp's bias slices (tables written by preceding small kernels: coherent loads)
-        const volatile float* hsrc = p.hid_bias + (size_t)img * 128 + half * 64;
-        const volatile float* isrc = p.img_bias + (size_t)img * 64 + half * 32;
-        __syncwarp();
-        hb[lane] = hsrc[lane]; hb[lane + 32] = hsrc[lane + 32];
-        wb[lane] = isrc[lane];
-        if (p.res_bias) {
-          const volatile float* rsrc = p.res_bias + (size_t)img * 64 + half * 32;
-          wb[32 + lane] = rsrc[lane];
+    if (e < 4) {
+      // ---------- convert: 16 pieces of 8 channels per thread (row r of both K blocks of P)
+      int buf1 = 0; uint32_t acc1_ph = 0, pph = 0;
+      const uint32_t sw = (uint32_t)(r & 7);
+      float* hb = s_hb + e * 128;
+      for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+        const int img = tile / tiles_per_img;
+        {                                          // hidden-bias row of this image (written by a preceding small kernel)
+          const volatile float* hsrc = p.hid_bias + (size_t)img * 128;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hb[lane + 32 * i] = hsrc[lane + 32 * i];
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      // ---- hidden accumulator -> P (8 pieces of 8 channels per warp)
-      ptx::mbar_wait(&acc1_full[buf1], acc1_ph);
-      ptx::mbar_wait(&p_empty[half], pph ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf1 * kAcc1Stride);
+        ptx::mbar_wait(&acc1_full[buf1], acc1_ph);
+        ptx::mbar_wait(&p_empty[0], pph ^ 1);      // the projection of the previous tile has read P
+        ptx::mbar_wait(&p_empty[1], pph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf1 * kAcc1Stride);
 #pragma unroll 1
-      for (int pc = 0; pc < 8; ++pc) {
-        const int col = p.piece_col[half * 8 + pc];
-        uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
-        if (col >= 0) {                            // warp-uniform
-          uint32_t acc[8];
-          ptx::tmem_ld_32x32b_x8(tmem_acc + col, acc);
-          ptx::tmem_ld_wait();
+        for (int pp = 0; pp < 16; ++pp) {
+          const int col = p.piece_col[pp];
+          uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
+          if (col >= 0) {                          // warp-uniform
+            uint32_t acc[8];
+            ptx::tmem_ld_32x32b_x8(tmem_acc + col, acc);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x0 = fmaxf(__uint_as_float(acc[2 * i]) + hb[pc * 8 + 2 * i], 0.f);
-            const float x1 = fmaxf(__uint_as_float(acc[2 * i + 1]) + hb[pc * 8 + 2 * i + 1], 0.f);
-            const uint32_t h = ptx::pack_bf16x2(x0, x1);
-            hw[i] = h;
-            lw[i] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
-          }
-        }
-        const uint32_t c0 = ((uint32_t)pc ^ sw) << 4;
-        *reinterpret_cast<uint4*>(p_hi + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(p_lo + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc1_empty[buf1]), 0));
-        ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&p_full[half]), 0));
-      }
-      pph ^= 1;
-      if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
-
-      // ---- final: out = relu(acc2 + bias) + residual, 32 channels per warp
-      const bool valid = oy < p.H && ox < p.W;
-      const size_t pix = ((size_t)img * p.H + oy) * p.W + ox;
-      uint32_t rh[2][8], rl[2][8];
-      if (!p.has_res_proj && valid) {              // identity residual: requested before waiting for the accumulators
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const size_t off = pix * p.res_cstride + half * 32 + j * 16;
-          ptx::ld_global_v8(p.res_hi + off, rh[j]);
-          ptx::ld_global_v8(p.res_lo + off, rl[j]);
-        }
-      }
-      ptx::mbar_wait(acc2_full, t2ph);
-      ptx::tc_fence_after();
-      t2ph ^= 1;
-      const uint32_t tmem_2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kAcc2Col + half * 32);
-      const uint32_t tmem_3 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kAcc3Col + half * 32);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t acc[16], acc3[16];
-        ptx::tmem_ld_32x32b_x16(tmem_2 + j * 16, acc);
-        if (p.has_res_proj) ptx::tmem_ld_32x32b_x16(tmem_3 + j * 16, acc3);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[i]) + wb[j * 16 + i], 0.f);
-          if (p.has_res_proj) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(acc3[i]) + wb[32 + j * 16 + i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[2 * i] += __uint_as_float(rh[j][i] << 16) + __uint_as_float(rl[j][i] << 16);
-              v[2 * i + 1] += __uint_as_float(rh[j][i] & 0xFFFF0000u) + __uint_as_float(rl[j][i] & 0xFFFF0000u);
+            for (int i = 0; i < 4; ++i) {
+              const float x0 = fmaxf(__uint_as_float(acc[2 * i]) + hb[pp * 8 + 2 * i], 0.f);
+              const float x1 = fmaxf(__uint_as_float(acc[2 * i + 1]) + hb[pp * 8 + 2 * i + 1], 0.f);
+              const uint32_t h = ptx::pack_bf16x2(x0, x1);
+              hw[i] = h;
+              lw[i] = ptx::pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
             }
           }
-          uint32_t hw[8], lw[8];
+          unsigned char* dst = p_buf + (size_t)(pp >> 3) * 2 * kBlkPPlane + (size_t)r * 128 + ((((uint32_t)pp & 7u) ^ sw) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(dst + kBlkPPlane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc1_empty[buf1]), 0));
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&p_full[0]), 0));
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&p_full[1]), 0));
+        }
+        pph ^= 1;
+        if (++buf1 == 2) { buf1 = 0; acc1_ph ^= 1; }
+      }
+    } else {
+      // ---------- finish: out = relu(acc2 + bias) + residual, all 64 channels of row r, per-image column sums
+      uint32_t t2ph = 0;
+      float* wb = s_wb + (e - 4) * 128;            // img_bias (64) | res_bias (64)
+      float sacc[64];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t h = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            hw[i] = h;
-            lw[i] = ptx::pack_bf16x2(v[2 * i] - __uint_as_float(h << 16), v[2 * i + 1] - __uint_as_float(h & 0xFFFF0000u));
+      for (int i = 0; i < 64; ++i) sacc[i] = 0.f;
+      int sum_img = -1;
+      auto flush_sums = [&](int img_) {            // per column: sum over the 32 lanes (once per image and warp)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float v = sacc[i];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if (lane == (i & 31)) p.sum_part[(((size_t)blockIdx.x * 4 + q) * p.n_img + img_) * 64 + i] = v;
+          sacc[i] = 0.f;
+        }
+      };
+      for (int tile = cta; tile < p.n_tiles; tile += n_cta) {
+        const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
+        const int oy = (rem / p.tiles_x) * 16 + (int)rank * 8 + (r >> 4), ox = (rem % p.tiles_x) * 16 + (r & 15);
+        if (p.sum_part && img != sum_img) {        // tiles come in image order
+          if (sum_img >= 0) flush_sums(sum_img);
+          sum_img = img;
+        }
+        {
+          const volatile float* isrc = p.img_bias + (size_t)img * 64;
+          __syncwarp();
+          wb[lane] = isrc[lane]; wb[lane + 32] = isrc[lane + 32];
+          if (p.res_bias) {
+            const volatile float* rsrc = p.res_bias + (size_t)img * 64;
+            wb[64 + lane] = rsrc[lane]; wb[96 + lane] = rsrc[lane + 32];
           }
-          const size_t off = pix * p.out_cstride + half * 32 + j * 16;
-          ptx::st_global_v8(p.out_hi + off, hw);
-          ptx::st_global_v8(p.out_lo + off, lw);
-          if (p.sum_part) {
+          __syncwarp();
+        }
+        const bool valid = oy < p.H && ox < p.W;
+        const size_t pix = ((size_t)img * p.H + oy) * p.W + ox;
+        ptx::mbar_wait(acc2_full, t2ph);
+        ptx::tc_fence_after();
+        t2ph ^= 1;
+        const uint32_t tmem_2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kAcc2Col;
+        const uint32_t tmem_3 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kAcc3Col;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sacc[j * 16 + i] += v[i];
+        for (int j = 0; j < 4; ++j) {
+          uint32_t acc[16], acc3[16], rh[8], rl[8];
+          if (!p.has_res_proj && valid) {          // identity residual: the block's input planes
+            const size_t off = pix * p.res_cstride + j * 16;
+            ptx::ld_global_v8(p.res_hi + off, rh);
+            ptx::ld_global_v8(p.res_lo + off, rl);
+          }
+          ptx::tmem_ld_32x32b_x16(tmem_2 + j * 16, acc);
+          if (p.has_res_proj) ptx::tmem_ld_32x32b_x16(tmem_3 + j * 16, acc3);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(acc[i]) + wb[j * 16 + i], 0.f);
+            if (p.has_res_proj) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(acc3[i]) + wb[64 + j * 16 + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[2 * i] += __uint_as_float(rh[i] << 16) + __uint_as_float(rl[i] << 16);
+                v[2 * i + 1] += __uint_as_float(rh[i] & 0xFFFF0000u) + __uint_as_float(rl[i] & 0xFFFF0000u);
+              }
+            }
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t h = ptx::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              hw[i] = h;
+              lw[i] = ptx::pack_bf16x2(v[2 * i] - __uint_as_float(h << 16), v[2 * i + 1] - __uint_as_float(h & 0xFFFF0000u));
+            }
+            const size_t off = pix * p.out_cstride + j * 16;
+            ptx::st_global_v8(p.out_hi + off, hw);
+            ptx::st_global_v8(p.out_lo + off, lw);
+            if (p.sum_part) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sacc[j * 16 + i] += v[i];
+            }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc2_empty), 0));
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc2_empty), 0));
+      if (p.sum_part && sum_img >= 0) flush_sums(sum_img);
     }
-    if (p.sum_part && sum_img >= 0) flush_sums(sum_img);
   }
   ptx::tc_fence_before();
   __syncthreads();
