@@ -23,8 +23,8 @@ def num(r, idx, k):
 
 def conv(rep, dst):
     idx, units, data = raw(rep)
-    L = ["ncu --set full --clock-control none: conv_igemm_kernel<BN, PAIR, STACK> launches of one perceive step (B=4),",
-         "in launch order: the temporal model's convs, then the first decoder convs.  Cold cache, serialised.",
+    L = ["ncu --set full --clock-control none: tensor-core launches of one perceive step (B=4) in launch order: the temporal",
+         "model (entry conv + block_fused per TemporalBlock, aspp_fused x2 = DeepLab head), then the first decoder convs.  Cold cache.",
          "PAIR=1: tcgen05.mma.cta_group::2 tiling; STACK=1: stacked [W_hi; W_lo] operand.  dram = dram__bytes_read/write.sum,",
          "L2->SM = lts__t_sectors_srcunit_tex_op_read.sum * 32 B.",
          f"{'#':>2} {'kernel':24s} {'grid':>5} {'us':>8} {'dramRd MB':>10} {'dramWr MB':>10} {'L2->SM GB':>10} {'L2->SM TB/s':>12} {'regs':>5}"]
@@ -32,7 +32,7 @@ def conv(rep, dst):
     for i, r in enumerate(data):
         name = r[idx["Kernel Name"]]
         short = name.split("conv_igemm_kernel")[1].split("(")[0] if "conv_igemm" in name else \
-            ("  aspp_fused" if "aspp_fused" in name else name[:20])
+            ("  aspp_fused" if "aspp_fused" in name else "  block_fused" if "block_fused" in name else name[:20])
         t = num(r, idx, "gpu__time_duration.sum")
         rd, wr = num(r, idx, "dram__bytes_read.sum"), num(r, idx, "dram__bytes_write.sum")
         l2 = num(r, idx, "lts__t_sectors_srcunit_tex_op_read.sum") * 32 / 1e9

@@ -17,7 +17,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --profiler-range > gpurun_out/${tag}_ncu_bench.log 2>&1
 wc -l gpurun_out/${tag}_launches.csv
 # full-section captures: the conv kernels of the temporal model (18) + first decoder convs, and the lift-splat kernels
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"conv_igemm|aspp_fused" -c 20 \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"conv_igemm|aspp_fused|block_fused" -c 16 \
     -o gpurun_out/${tag}_conv_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-pipeline --profiler-range \
     > gpurun_out/${tag}_ncu_conv.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"lift_splat|bev_finalize" -c 2 \
