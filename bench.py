@@ -289,7 +289,7 @@ def run_reference_arm(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-OUR_KERNELS = ("conv_igemm", "aspp_fused", "lift_splat", "bev_finalize", "bev_discount", "pool_reduce", "pool_bias", "small_linear",
+OUR_KERNELS = ("conv_igemm", "aspp_fused", "block_fused", "lift_splat", "bev_finalize", "bev_discount", "pool_reduce", "pool_bias", "small_linear",
                "upsample2x", "col_sum_reduce", "hilo", "spatial_sum", "clear_bytes", "lift_splat_bwd")
 
 
@@ -310,7 +310,7 @@ def count_launches(step_fn, dev):
             total += 1
             if any(k in ev.name for k in OUR_KERNELS):
                 ours += 1
-            if "conv_igemm" in ev.name or "aspp_fused" in ev.name:
+            if "conv_igemm" in ev.name or "aspp_fused" in ev.name or "block_fused" in ev.name:
                 conv_us += float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
         return ours, total, conv_us * 1e-3
     except Exception as e:                                  # CUPTI unavailable: say so instead of guessing
@@ -603,7 +603,7 @@ def main():
                 if args.workload in ("perceive", "perceive_heads") else None
             ach = flops / (dense_ms * 1e-3) / 1e12 if flops and dense_ms > 0 else None
             line["stage_ms"] = stage_ms
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> + aspp_fused_kernel (temporal model + decoder)",
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN, PAIR, STACK> + aspp_fused_kernel + block_fused_kernel (temporal model + decoder)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"] if ach else None, "peak_source": pk["source"],
                                 "traffic": TRAFFIC["conv"]["bytes_per_sample"] * b if args.workload == "perceive" else None,
@@ -636,7 +636,7 @@ def main():
 # committed `ncu --set full` captures, per sample
 TRAFFIC = {
     "lift_splat": {"bytes_per_sample": int(263.6e6 / 4), "source": "static: profiles/r02_ncu_liftsplat_v2_summary.txt (scatter 108.7 MB + finalize 155.0 MB, B=4)"},
-    "conv": {"bytes_per_sample": int(3779e6 / 4), "source": "static: profiles/r02_ncu_conv_v2_summary.txt (the temporal model's 10 launches incl. the two B2B launches + first 10 decoder convs of 35, cold cache, B=4)"},
+    "conv": {"bytes_per_sample": int(2464e6 / 4), "source": "static: profiles/r02_ncu_conv_v3_summary.txt (the temporal model's 6 tensor-core launches incl. the four B2B launches + the first 10 decoder convs of 35, cold cache, B=4)"},
 }
 
 
