@@ -485,6 +485,7 @@ def main():
         barrier()
         return parallel.max_over_ranks(t0.elapsed_time(t1), dev)
 
+    _progress("setup done")
     for _ in range(W):
         step_resident()
     # parity gate: the step that is about to be timed must produce the reference's logits
@@ -498,7 +499,9 @@ def main():
         sampler.start()
     if args.profiler_range:
         torch.cuda.cudart().cudaProfilerStart()
+    _progress("timing resident steps")
     total_ms = timed(step_resident, K)
+    _progress("timing e2e")
     if args.profiler_range:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
@@ -514,7 +517,24 @@ def main():
             step_e2e()
         e2e_ms = timed(step_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
+    # the host link: what one pinned host->device copy of the step's inputs achieves on this box (the e2e figure cannot beat it)
+    link_gbs = None
+    if rank == 0:
+        big = host["feat"]
+        dst = torch.empty_like(big, device=dev)
+        for _ in range(2):
+            dst.copy_(big, non_blocking=True)
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            dst.copy_(big, non_blocking=True)
+        c.record()
+        torch.cuda.synchronize()
+        link_gbs = 5 * big.numel() * big.element_size() / (a.elapsed_time(c) * 1e-3) / 1e9
+        del dst
 
+    _progress("sustained")
     # sustained figure: the same resident step back to back for >= 2 s (the 20-step region above is a ~65 ms burst)
     sustained = None
     if not args.no_extras:
@@ -523,6 +543,7 @@ def main():
         sustained = {"value": b * world / (sus_ms / n_sus * 1e-3), "unit": UNIT, "steps": n_sus,
                      "ms_per_step": sus_ms / n_sus, "seconds": sus_ms * 1e-3}
 
+    _progress("stages")
     # per-stage device time: each stage captured as its own CUDA graph (no launch gaps), timed with CUDA events
     stage_ms = {}
     if perceive:
@@ -530,6 +551,7 @@ def main():
                                heads=heads)
     ours, total_launches, conv_ms_prof = count_launches(step_resident, dev)
 
+    _progress("rigs")
     # the lift-splat on both rigs (level cameras = SURVEY 8d; 1 degree of roll / pitch / yaw error per camera)
     rigs = {}
     if not args.no_extras and args.workload in ("perceive", "lift_splat"):
@@ -551,13 +573,9 @@ def main():
             rigs[name] = {"ms": ms, "fast_path_fraction": fpf}
             del f, d, o
 
+    _progress("main measurements done")
     # latency mode (north_star): global batch 1 < #GPUs, camera frames sharded, ONE all-gather of raw BEV frames
-    latency = None
-    if world > 1 and perceive and not args.no_extras:
-        try:
-            latency = time_latency_mode(model, cfg, dev, flush, rank, world)
-        except Exception as e:            # never let the extra mode cost the main line
-            latency = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    run_latency = world > 1 and perceive and not args.no_extras
 
     if rank == 0:
         ms_per_step = total_ms / K
@@ -587,7 +605,9 @@ def main():
             "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks,
             "e2e": {"value": frames / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mode": e2e_mode},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mode": e2e_mode,
+                    "host_link_h2d_gbs": link_gbs,
+                    "h2d_ms_per_step_at_link_rate": (h2d / (link_gbs * 1e9) * 1e3) if link_gbs else None},
             "parity_checked": parity is not None, "parity": parity,
             "sustained": sustained,
         }
@@ -615,8 +635,7 @@ def main():
             line["roofline_lift_splat"] = roof_ls
         else:
             line["roofline"] = roof_ls
-        if latency is not None:
-            line["latency_mode"] = latency
+        _LINE["line"] = line
         if perceive and os.environ.get("STP3_TUNE_REPORT"):
             from stp3_b200 import dense
             for desc, times in dense.TUNE_LOG:
@@ -626,11 +645,37 @@ def main():
             r = arm.time(3, 1)
             line["cpu_baseline"] = {"value": r["fps"], "unit": UNIT, "cores": r["threads"], "kind": arm.kind,
                                     "sample": arm.describe(r, 3, 1)}
-        print(json.dumps(line), flush=True)
+    # the latency mode runs LAST and under a watchdog: whatever happens in it (a collective that never returns on some
+    # topology), rank 0 still prints its ONE JSON line and every rank exits 0
+    if run_latency:
+        import threading
+
+        def give_up():
+            if rank == 0:
+                _LINE["line"]["latency_mode"] = {"unavailable": "timed out after 120 s (watchdog)"}
+                print(json.dumps(_LINE["line"]), flush=True)
+            os._exit(0)
+        dog = threading.Timer(120.0, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            latency = time_latency_mode(model, cfg, dev, flush, rank, world)
+        except Exception as e:            # never let the extra mode cost the main line
+            latency = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        dog.cancel()
+        if rank == 0:
+            _LINE["line"]["latency_mode"] = latency
+    if rank == 0:
+        print(json.dumps(_LINE["line"]), flush=True)
     if world > 1:
         import torch.distributed as dist
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
+
+_LINE = {}
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) cannot be measured outside ncu: static values from the
 # committed `ncu --set full` captures, per sample
@@ -638,6 +683,11 @@ TRAFFIC = {
     "lift_splat": {"bytes_per_sample": int(263.6e6 / 4), "source": "static: profiles/r02_ncu_liftsplat_v2_summary.txt (scatter 108.7 MB + finalize 155.0 MB, B=4)"},
     "conv": {"bytes_per_sample": int(2464e6 / 4), "source": "static: profiles/r02_ncu_conv_v3_summary.txt (the temporal model's 6 tensor-core launches incl. the four B2B launches + the first 10 decoder convs of 35, cold cache, B=4)"},
 }
+
+
+def _progress(msg):
+    if os.environ.get("STP3_BENCH_PROGRESS"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() % 1000:.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
@@ -652,10 +702,12 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
     X, Y = cfg.bev_xy
     S, C = cfg.receptive_field, cfg.out_channels
     with torch.no_grad():
+        _progress("latency: eager nccl warm-up")
         for _ in range(3):
             sh = model.forward_features_frame_sharded(*a)
             full = model.forward_features(*a)
         torch.cuda.synchronize()
+        _progress("latency: eager nccl timed")
         err = max(float((sh[k] - full[k]).abs().max() / full[k].abs().max()) for k in ("segmentation", "pedestrian", "hdmap"))
 
         def timed(fn):
@@ -674,6 +726,7 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
         # the all-gather fused into the finalize kernel's epilogue (peer stores over NVLink, symmetric memory)
         peer = None
         try:
+            _progress("latency: peer warm-up (symmetric memory rendezvous)")
             for _ in range(3):
                 shp = model.forward_features_frame_sharded(*a, gather="peer")
             torch.cuda.synchronize()
@@ -698,10 +751,12 @@ def time_latency_mode(model, cfg, dev, flush, rank, world, reps=10):
                                           f0s, fcs, workspace=model._ws, peer_ptrs=pf.ptrs)
                 pf.barrier()
                 ops.bev_discount(pf.buf.view(1, S, X, Y, C), float(model.discount))
+            _progress("latency: lift stage both ways")
             for _ in range(2):
                 lift_nccl(); lift_peer()
             # both as ONE CUDA graph (what a latency-critical deployment would run): unsharded vs frame-sharded + peer stores
             graphed = None
+            _progress("latency: graph capture")
             try:
                 from stp3_b200.models.stp3 import GraphedPerception
                 g_full = GraphedPerception(model, 1, cfg.n_cameras, dev, entry="lift")
