@@ -111,12 +111,9 @@ struct ConvSmem {
   // B_hi + B_lo of one K step; a stacked pair holds [own half of the stacked operand (BN rows)][own half of W_hi]
   static constexpr int kBTileBytes = (STACK && PAIR ? 3 : 2) * kBRows * kBK * 2;
   static constexpr int kAccCols = STACK ? 2 * BN : BN;                 // TMEM columns of one accumulator
-  static constexpr int kSubSlots = PAIR ? 1 : 2;                       // sub-tile accumulators per buffer (a pair has one)
-  static constexpr int kTmemColsRaw = 2 * kSubSlots * kAccCols;        // x 2 accumulator buffers
-  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128 :
-                                   kTmemColsRaw <= 256 ? 256 : 512;   // allocations are powers of two
+  static constexpr int kTmemCols = 4 * kAccCols;                       // 2 sub-tiles x 2 accumulator buffers
   static constexpr size_t tail_bytes() {
-    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + kEpiWarps * 128 * sizeof(float) +
+    return (1 + kMaxHeadOut) * BN * sizeof(float) + kMaxHeadOut * 128 * sizeof(float) + kEpiWarps * 64 * sizeof(float) +
            (2 * kMaxAStages + 2 * kMaxBStages + 8) * 8;
   }
 };
@@ -154,7 +151,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using S = ConvSmem<BN, PAIR, STACK>;
   static_assert(!STACK || BN == 64, "stacked weight operand: BN = 64 only (TMEM columns)");
-  static_assert(BN <= 128 || PAIR, "256 output columns: CTA pairs only (TMEM columns, weight tile per CTA)");
   const int kBRows = p.b_rows;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;              // 0 = leader
   const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a pair walks together)
@@ -171,8 +167,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(b_ring + (size_t)(resident ? k_iters : p.nb_stages) * p.b_tile_bytes);
   float* s_head = s_bias + BN;                    // [kMaxHeadOut][BN]
   float* s_hx = s_head + kMaxHeadOut * BN;        // [kMaxHeadOut][128] head partials handed between column halves
-  float* s_wb = s_hx + kMaxHeadOut * 128;         // [kEpiWarps][128] per-image bias slice of each epilogue warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + kEpiWarps * 128);
+  float* s_wb = s_hx + kMaxHeadOut * 128;         // [kEpiWarps][64] per-image bias slice of each epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + kEpiWarps * 64);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxAStages;
   uint64_t* b_full = a_empty + kMaxAStages;
@@ -344,7 +340,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 // sub-tile rows [sub*8, sub*8+8) of the tile, shifted by j image rows inside the loaded box
                 const uint32_t a_hi = a_hi0 + (uint32_t)((j * kTileW + sub * 128) * 128);
                 const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), da_lo = ptx::umma_desc_k_sw128(a_hi + p.a_plane_bytes);
-                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * S::kSubSlots + sub) * S::kAccCols);
+                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + sub) * S::kAccCols);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                   if (k < k_begin || k >= k_end) continue;                 // K steps of pure channel padding
@@ -454,7 +450,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       const float* bsrc = s_bias;                 // bias of column c at bsrc[c]
       if (p.img_bias) {
         const float* ib = p.img_bias + (size_t)img * p.img_bias_stride + col0;
-        float* wb = s_wb + e * 128;
+        float* wb = s_wb + e * 64;
         __syncwarp();                             // every lane is done with the previous tile's slice
 #pragma unroll
         for (int i = lane; i < kColsPerWarp; i += 32) wb[i] = *(reinterpret_cast<const volatile float*>(ib) + i);
@@ -471,7 +467,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         float hacc[kMaxHeadOut];
 #pragma unroll
         for (int k = 0; k < kMaxHeadOut; ++k) hacc[k] = 0.f;
-        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * S::kSubSlots + sub) * S::kAccCols + col0);
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * S::kAccCols + col0);
 #pragma unroll 1
         for (int j = 0; j < kColsPerWarp / 16; ++j) {
           const int cb = col0 + j * 16;              // first output channel of this chunk
@@ -789,10 +785,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
       return set_error(STP3_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d %d", (int)r1, (int)r2);
   }
   const int kblocks = d->cin / kBK;
-  // 256 output channels: one launch of a CTA pair (UMMA M = 256, N = 256: every activation tile is fetched once), or two
-  // 128-column launches for the single-CTA tilings
-  static const bool bn256 = [] { const char* e = getenv("STP3_CONV_BN256"); return !e || atoi(e) != 0; }();
-  const int bn_launch = d->bn == 256 ? (pair && bn256 ? 256 : 128) : d->bn;
+  const int bn_launch = d->bn == 256 ? 128 : d->bn;     // 256 output channels run as two 128-column launches
   // the MMAs cover only the columns that carry weights (n_cols, rounded up to the UMMA granularity of 16)
   const int n_mma = d->bn <= 128 && d->n_cols > 0 && d->n_cols < d->bn ? ((d->n_cols + 15) / 16) * 16 : bn_launch;
   {
@@ -951,8 +944,6 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
     if (bn_launch == 64) {
       if (stack) { if (pair) STP3_LAUNCH_CONV(64, true, true); else STP3_LAUNCH_CONV(64, false, true); }
       else { if (pair) STP3_LAUNCH_CONV(64, true, false); else STP3_LAUNCH_CONV(64, false, false); }
-    } else if (bn_launch == 256) {
-      STP3_LAUNCH_CONV(256, true, false);
     } else {
       if (pair) STP3_LAUNCH_CONV(128, true, false); else STP3_LAUNCH_CONV(128, false, false);
     }
