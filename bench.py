@@ -369,6 +369,9 @@ def main():
                     help="bracket the resident timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     cfg = syn.CONFIGS["stress" if args.workload == "stress" else "perceive"]
+    if os.environ.get("STP3_BENCH_DUMP_AFTER"):      # debugging aid: Python stacks of every thread after N seconds, then exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["STP3_BENCH_DUMP_AFTER"]), exit=True)
 
     if args.impl == "reference":
         run_reference_arm(args, cfg)
