@@ -20,6 +20,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import torch
@@ -463,10 +464,24 @@ def main():
     def timed(fn, steps):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
+        issued = [0]
+        stop = None
+        if os.environ.get("STP3_BENCH_MONITOR") and steps > 50:     # hang diagnosis: device progress once a second
+            stop = threading.Event()
+
+            def watch():
+                while not stop.wait(1.0):
+                    n = issued[0]
+                    done = sum(1 for i in range(n) if evs[i][1].query())
+                    _progress(f"monitor: issued {n}/{steps}, finished on device {done}")
+            threading.Thread(target=watch, daemon=True).start()
         for s, e in evs:
             flush.zero_()                      # evict L2 between timed iterations (not timed)
             s.record(); fn(); e.record()
+            issued[0] += 1
         barrier()
+        if stop is not None:
+            stop.set()
         return parallel.max_over_ranks(sum(s.elapsed_time(e) for s, e in evs), dev)
 
     def timed_pipelined(pipe, steps):
