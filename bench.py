@@ -470,6 +470,7 @@ def main():
             stop = threading.Event()
 
             def watch():
+                torch.cuda.set_device(dev)
                 while not stop.wait(1.0):
                     n = issued[0]
                     done = sum(1 for i in range(n) if evs[i][1].query())
@@ -666,7 +667,6 @@ def main():
     # the latency mode runs LAST and under a watchdog: whatever happens in it (a collective that never returns on some
     # topology), rank 0 still prints its ONE JSON line and every rank exits 0
     if run_latency:
-        import threading
 
         def give_up():
             if rank == 0:
