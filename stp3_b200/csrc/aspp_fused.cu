@@ -39,6 +39,7 @@ constexpr int kPPlane = 128 * 128;                // 128 pixel rows x 64 bf16
 constexpr int kAsppHidden = 128;
 
 struct AsppParams {
+  int early_trigger;       // debug switch: griddepcontrol.launch_dependents at the top of the kernel
   int n_img, T, T_total, H, W;
   int tiles_x, tiles_y, n_tiles;
   int kblocks;
@@ -86,7 +87,7 @@ aspp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ptx::griddep_launch_dependents();
+  if (p.early_trigger) ptx::griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi); ptx::prefetch_tmap(&tm_a_lo); ptx::prefetch_tmap(&tm_w);
     for (int i = 0; i < kAsppNA; ++i) { ptx::mbar_init(&a_full[i], 2); ptx::mbar_init(&a_empty[i], 1); }
@@ -447,7 +448,11 @@ extern "C" int stp3_aspp_fused_fwd(const stp3_aspp_desc* d, const void* x_hi, co
   if (cfg.gridDim.x > 2u * (unsigned)max_clusters) cfg.gridDim.x = 2u * (unsigned)max_clusters;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = stp3_pdl_enabled("STP3_FUSED_PDL") ? 2 : 1;
+  {
+    static const bool early = [] { const char* e = getenv("STP3_FUSED_EARLY_TRIGGER"); return !e || atoi(e) != 0; }();
+    p.early_trigger = early ? 1 : 0;
+  }
   STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, aspp_fused_kernel, tm_hi, tm_lo, tm_w, p));
   STP3_CUDA_OK(cudaGetLastError());
   return STP3_OK;

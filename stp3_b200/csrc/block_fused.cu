@@ -50,6 +50,7 @@ struct BlkChain {
 };
 
 struct BlkParams {
+  int early_trigger;       // debug switch: griddepcontrol.launch_dependents at the top of the kernel
   int n_img, T, H, W;
   int tiles_x, tiles_y, n_tiles;
   int n_chain;
@@ -108,7 +109,7 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tm_m_hi, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ptx::griddep_launch_dependents();
+  if (p.early_trigger) ptx::griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_m_hi); ptx::prefetch_tmap(&tm_m_lo); ptx::prefetch_tmap(&tm_x_hi); ptx::prefetch_tmap(&tm_x_lo);
     ptx::prefetch_tmap(&tm_w);
@@ -605,7 +606,11 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   }
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = stp3_pdl_enabled("STP3_FUSED_PDL") ? 2 : 1;
+  {
+    static const bool early = [] { const char* e = getenv("STP3_FUSED_EARLY_TRIGGER"); return !e || atoi(e) != 0; }();
+    p.early_trigger = early ? 1 : 0;
+  }
   STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, block_fused_kernel, tm[0], tm[1], tm[2], tm[3], tm_w, p));
   STP3_CUDA_OK(cudaGetLastError());
   if (col_sums) return launch_col_sum_reduce(p.sum_part, (int)cfg.gridDim.x * 4, p.n_img, col_sums, stream);

@@ -33,6 +33,15 @@ int launch_col_sum_reduce(const float* part, int n_part, int n_img, float* out, 
 
 }  // namespace stp3
 
+// Debug switches: STP3_PDL=0 turns programmatic dependent launch off everywhere, `family`=0 (STP3_CONV_PDL,
+// STP3_FUSED_PDL, STP3_AUX_PDL) for one kernel family.
+static inline bool stp3_pdl_enabled(const char* family) {
+  const char* all = getenv("STP3_PDL");
+  if (all && atoi(all) == 0) return false;
+  const char* e = getenv(family);
+  return !e || atoi(e) != 0;
+}
+
 // Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains; it MUST
 // execute griddepcontrol.wait (ptx::griddep_wait) before touching global memory the predecessor produced.
 template <typename... KArgs, typename... Args>
@@ -43,7 +52,7 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = stp3_pdl_enabled("STP3_AUX_PDL") ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

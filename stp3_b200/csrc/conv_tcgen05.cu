@@ -735,7 +735,7 @@ extern "C" int stp3_conv_fwd(const stp3_conv_desc* d, const void* x_hi, const vo
   const int want_nsub = d->tune_n_sub ? d->tune_n_sub : env_nsub;
   const int want_group_raw = d->tune_group ? d->tune_group : env_group;
   const int want_group = want_group_raw & 3;
-  static const bool use_pdl = [] { const char* e = getenv("STP3_CONV_PDL"); return !e || atoi(e) != 0; }();
+  static const bool use_pdl = stp3_pdl_enabled("STP3_CONV_PDL");
   const bool stream_weights = (want_group_raw & 4) != 0;    // +4: keep the weights in the ring even if they would fit
   // +8: stacked [W_hi; W_lo] operand (bn = 64 only).  Untuned (tune_group == 0) multi-tap 64-column layers use it: it
   // won on every such layer of the hot path (profiles/r01_autotune_v9.txt)
