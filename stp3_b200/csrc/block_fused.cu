@@ -608,7 +608,11 @@ extern "C" int stp3_block_fused_fwd(const stp3_block_desc* d, const void* mid_hi
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.numAttrs = stp3_pdl_enabled("STP3_FUSED_PDL") ? 2 : 1;
   {
-    static const bool early = [] { const char* e = getenv("STP3_FUSED_EARLY_TRIGGER"); return !e || atoi(e) != 0; }();
+    // No early griddepcontrol.launch_dependents from the back-to-back kernels: with it, a chain block_fused -> col_sum_reduce
+    // -> pool_bias -> aspp_fused in flight at once stopped making progress about once in 400 .. 2000 replayed steps
+    // (tools/hang_probe.py; 20000 replays are clean without it and with programmatic launch off altogether).  The
+    // dependents are released when the grid completes; this kernel itself still starts early behind its predecessor.
+    static const bool early = [] { const char* e = getenv("STP3_FUSED_EARLY_TRIGGER"); return e && atoi(e) != 0; }();
     p.early_trigger = early ? 1 : 0;
   }
   STP3_CUDA_OK(cudaLaunchKernelEx(&cfg, block_fused_kernel, tm[0], tm[1], tm[2], tm[3], tm_w, p));
