@@ -390,8 +390,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner to STDOUT at the VERSION and WARN levels; rank 0's stdout is ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     W, K, b = max(args.warmup, 3), args.steps, args.batch
     perceive = args.workload in PERCEPTION
