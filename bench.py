@@ -574,17 +574,7 @@ def main():
                     "h2d_ms_per_step_at_link_rate": (h2d / (link_gbs * 1e9) * 1e3) if link_gbs else None},
             "parity_checked": parity is not None, "parity": parity,
         }
-    extras_limit = float(os.environ.get("STP3_BENCH_EXTRAS_LIMIT", "600" if world == 1 else "300"))
-
-    def give_up():
-        if rank == 0:
-            _LINE["line"]["extras"] = {"unavailable": f"timed out after {extras_limit:.0f} s (watchdog): the keys after "
-                                                      "'parity' are missing or partial"}
-            print(json.dumps(_LINE["line"]), flush=True)
-        os._exit(0)
-    dog = threading.Timer(extras_limit, give_up)
-    dog.daemon = True
-    dog.start()
+    dog = extras_watchdog(float(os.environ.get("STP3_BENCH_EXTRAS_LIMIT", "600" if world == 1 else "300")), rank)
 
     _progress("sustained")
     # sustained figure: the same resident step back to back for >= 2 s (the 20-step region above is a ~65 ms burst)
@@ -703,6 +693,21 @@ def main():
 
 
 _LINE = {}
+
+
+def extras_watchdog(limit_s, rank, exit_fn=os._exit, out=None):
+    """Timer armed once the contract line exists (_LINE["line"] on rank 0): if the explanatory part of the run has not
+    cancelled it after `limit_s` seconds, rank 0 prints the line as it stands -- marked -- and every rank exits 0."""
+    def give_up():
+        if rank == 0:
+            _LINE["line"]["extras"] = {"unavailable": f"timed out after {limit_s:.0f} s (watchdog): the keys after "
+                                                      "'parity' are missing or partial"}
+            print(json.dumps(_LINE["line"]), file=out or sys.stdout, flush=True)
+        exit_fn(0)
+    dog = threading.Timer(limit_s, give_up)
+    dog.daemon = True
+    dog.start()
+    return dog
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) cannot be measured outside ncu: static values from the
 # committed `ncu --set full` captures, per sample

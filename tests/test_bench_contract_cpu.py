@@ -44,3 +44,33 @@ def test_reference_arm_uses_the_installed_reference_when_present():
 def test_b200_arm_has_no_cpu_fallback():
     r = run("--steps", "1", "--warmup", "3", "--no-cpu-baseline", timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_extras_watchdog_prints_the_line_it_has():
+    """Once the timed regions are done the contract line exists; if the explanatory part (sustained loop, stage graphs,
+    latency mode ...) never comes back, rank 0 prints that line with a note and every rank exits 0."""
+    import io
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    exits = []
+    for rank in (0, 1):
+        bench._LINE["line"] = {"metric": "bev_frames_per_sec", "value": 1.0}
+        buf = io.StringIO()
+        dog = bench.extras_watchdog(0.05, rank, exit_fn=exits.append, out=buf)
+        dog.join(5)
+        time.sleep(0.05)
+        lines = [l for l in buf.getvalue().splitlines() if l.strip()]
+        if rank == 0:
+            assert len(lines) == 1
+            d = json.loads(lines[0])
+            assert d["value"] == 1.0 and "timed out" in d["extras"]["unavailable"]
+        else:
+            assert lines == []
+    assert exits == [0, 0]
+    # cancelled in time: nothing is printed, nobody exits
+    buf = io.StringIO()
+    dog = bench.extras_watchdog(0.2, 0, exit_fn=exits.append, out=buf)
+    dog.cancel()
+    time.sleep(0.4)
+    assert buf.getvalue() == "" and exits == [0, 0]

@@ -71,15 +71,17 @@ def _gather_worker(rank, world_size, port, n_frames, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames", [3, 6])
-def test_all_gather_frames_uneven_and_even(n_frames):
-    """Frame-sharded mode: flat frames b*S+t split over 2 ranks (3 frames -> 2 + 1) and gathered back in order."""
+@pytest.mark.parametrize("world_size,n_frames", [(2, 1), (2, 3), (2, 6), (4, 3)])
+def test_all_gather_frames_uneven_and_even(world_size, n_frames):
+    """Frame-sharded mode: flat frames b*S+t split over the ranks (3 frames on 2 ranks -> 2 + 1; on 4 ranks -> 1 + 1 + 1
+    + 0: ranks without a frame still take part in the exchange) and gathered back in order."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gather_worker, args=(r, 2, 29620 + n_frames, n_frames, q)) for r in range(2)]
+    port = 29620 + 10 * world_size + n_frames
+    procs = [ctx.Process(target=_gather_worker, args=(r, world_size, port, n_frames, q)) for r in range(world_size)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
