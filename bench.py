@@ -686,10 +686,14 @@ def main():
         print(json.dumps(_LINE["line"]), flush=True)
     if world > 1:
         import torch.distributed as dist
+        bye = threading.Timer(30.0, os._exit, args=(0,))      # the line is out: a stuck teardown must not keep the job alive
+        bye.daemon = True
+        bye.start()
         try:
             dist.destroy_process_group()
         except Exception:
             pass
+        bye.cancel()
 
 
 _LINE = {}
